@@ -1,0 +1,485 @@
+// acas2d_env.cuh -- one environment's step / reset / inject / extract, operating on state
+// held in registers and on the SoA arrays of include/acas2d_b200.h.  __host__ __device__
+// for the same reason as acas2d_math.cuh: tests/hostcheck compiles this file with g++ to
+// check the step orchestration against the CPU oracle; the product only runs it on the GPU.
+#pragma once
+
+#include <string.h>
+
+#include "../../include/acas2d_b200.h"
+#include "acas2d_math.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define ACAS_STCS(ptr, val) __stcs((ptr), (val))       /* streaming store: outputs are not re-read */
+#else
+#define ACAS_STCS(ptr, val) (*(ptr) = (val))
+#endif
+
+namespace acas2d {
+
+#if defined(__CUDACC__)
+typedef float4 Float4;
+#else
+struct alignas(16) Float4 { float x, y, z, w; };
+#endif
+
+struct StatePtrs {
+    Vec2d *ppos;
+    PlayerAux *paux;
+    Vec2d *tpos0;
+    Vec2d *tvel;
+    double *tpsi;
+    double *tvair;
+    uint32_t *episode_idx;
+    float *min_sep;
+    long long *stats;
+    uint64_t seed;
+    uint64_t gid0;
+    int64_t B;
+};
+
+struct Sinks {
+    float *obs;
+    float *reward;
+    uint8_t *done;
+    uint8_t *flags;
+    uint8_t *outcome;
+    float *term_obs;
+    float *ep_return;
+    int32_t *ep_length;
+};
+
+// ---------------------------------------------------------------- host-side parameter prep
+inline DevParams make_dev_params(const acas2d_params &p)
+{
+    DevParams d;
+    memset(&d, 0, sizeof(d));
+    const double dt = 1.0 / p.fps;                                  // aircraft.py:18
+    d.dt = dt;
+    d.airspeed = p.airspeed;
+    d.v_dt = p.airspeed * dt;
+    d.dpsi_per_action = p.acc_lat_limit / p.airspeed;               // aircraft.py:20-22 (Q1)
+    d.lookahead_rad = dt * kDeg2Rad;                                // kinematics.py:57-59 (Q2)
+    d.goal_x = p.goal_x; d.goal_y = p.goal_y;
+    d.coll_d2 = (2.0 * p.collision_radius) * (2.0 * p.collision_radius);   // game.py:187
+    d.goal_r2 = p.goal_radius * p.goal_radius;                      // game.py:192
+    d.width = p.width; d.height = p.height;
+    d.inv_360 = 1.0 / 360.0;
+    d.inv_d_dev_max = 1.0 / p.d_dev_max;
+    d.player_x0 = p.player_x0; d.player_y0 = p.player_y0;
+    d.player_psi_base = p.player_psi_base;
+    d.player_heading_lim = p.player_heading_lim;
+    d.traffic_heading_lim = p.traffic_heading_lim;
+    d.factor_min = p.airspeed_factor_min;
+    d.factor_span = p.airspeed_factor_max - p.airspeed_factor_min;
+    d.t0_x = p.width - p.collision_radius;                          // game.py:100
+    d.t0_y_up = p.collision_radius;                                 // game.py:101
+    d.t0_y_span = p.height - 2.0 * p.collision_radius;
+    d.tn_x_span = p.width - p.aircraft_size;                        // game.py:109
+    d.tn_y_span = 3.0 * p.height / 5.0;                             // game.py:110
+    d.inv_max_steps = (float)(1.0 / p.max_steps);
+    d.inv_d_goal_max = (float)(1.0 / p.d_goal_max);
+    d.inv_d_sep_max = (float)(1.0 / p.d_separation_max);
+    d.inv_d_cpa_max = (float)(1.0 / p.d_cpa_max);
+    d.vc_scale = (float)(p.fps / p.v_closing_max);
+    d.fps = (float)p.fps;
+    d.inv_safe_distance = (float)(1.0 / p.safe_distance);
+    const double d_goal_init = (p.width - p.goal_radius) - 2.0 * p.aircraft_size;   // rewards.py:22,46
+    d.rw_dev_max = (float)(d_goal_init / 2.0);
+    d.inv_rw_dev_max = (float)(2.0 / d_goal_init);
+    d.inv_rw_goal_max = (float)(1.0 / (d_goal_init + (p.airspeed / p.fps) * p.max_steps));
+    d.reward_goal = (float)p.reward_goal;
+    d.reward_collision = (float)p.reward_collision;
+    d.n_traffic = p.n_traffic;
+    d.max_steps = (int32_t)p.max_steps;
+    d.auto_reset = p.auto_reset;
+    d.uniform_speed = (p.airspeed_factor_min == p.airspeed_factor_max &&
+                       p.airspeed_factor_min == 1.0) ? 1 : 0;
+    return d;
+}
+
+inline StatePtrs make_state_ptrs(const acas2d_state &s)
+{
+    StatePtrs o;
+    o.ppos = (Vec2d *)s.ppos;
+    o.paux = (PlayerAux *)s.paux;
+    o.tpos0 = (Vec2d *)s.tpos0;
+    o.tvel = (Vec2d *)s.tvel;
+    o.tpsi = s.tpsi;
+    o.tvair = s.tvair;
+    o.episode_idx = s.episode_idx;
+    o.min_sep = s.min_sep;
+    o.stats = (long long *)s.stats;
+    o.seed = s.seed;
+    o.gid0 = s.env_id_offset;
+    o.B = s.num_envs;
+    return o;
+}
+
+// ---------------------------------------------------------------- episode statistics
+struct Tally {
+    int episodes, goal, coll, tout;
+    long long length, ret_fx, minsep_fx;
+};
+
+ACAS_HD void tally_clear(Tally &t)
+{
+    t.episodes = t.goal = t.coll = t.tout = 0;
+    t.length = t.ret_fx = t.minsep_fx = 0;
+}
+
+ACAS_HD void tally_add(Tally &t, int outcome, int steps, float ep_return, float minsep, bool has_minsep)
+{
+    t.episodes += 1;
+    t.goal += outcome == ACAS2D_OUTCOME_GOAL;
+    t.coll += outcome == ACAS2D_OUTCOME_COLLISION;
+    t.tout += outcome == ACAS2D_OUTCOME_TIMEOUT;
+    t.length += steps;
+    t.ret_fx += llrint((double)ep_return * ACAS2D_STAT_FX_SCALE);
+    if (has_minsep) t.minsep_fx += llrint((double)minsep * ACAS2D_STAT_FX_SCALE);
+}
+
+// ---------------------------------------------------------------- N_TRAFFIC == 1
+// ---------------------------------------------------------------- N_TRAFFIC == 1
+struct Env1 {
+    double px, py, psi;
+    int32_t steps;
+    float ret;
+    double t0x, t0y, tvx, tvy;
+    float minsep;
+    bool respawned;
+};
+
+ACAS_HD void store_obs8(float *row, const PlayerView &v, const Encounter &e, const DevParams &P)
+{
+    Float4 a; a.x = v.obs[0]; a.y = v.obs[1]; a.z = v.obs[2]; a.w = v.obs[3];
+    Float4 b; b.x = v.obs[4]; b.y = e.d * P.inv_d_sep_max; b.z = e.d_cpa * P.inv_d_cpa_max; b.w = e.v_c * P.vc_scale;
+    ACAS_STCS((Float4 *)row, a);
+    ACAS_STCS((Float4 *)row + 1, b);
+}
+
+// One environment step for a single-intruder env held in registers.
+// EMIT = write per-step outputs through `out`; i = local env index.
+template <bool MINSEP, bool EMIT>
+ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float action,
+                                          int64_t i, const Sinks &out, Tally &tally, float *reward_acc)
+{
+    // ---- game.action (game.py:222-247)
+    const double dpsi = (double)action * P.dpsi_per_action;               // game.py:225 + aircraft.py:20-22
+    Player p;
+    p.x = e.px; p.y = e.py;
+    player_set_heading(P, p, wrap360(e.psi + dpsi), dpsi);
+    player_advance(P, p);
+
+    Intruder t;
+    t.dx = e.tvx; t.dy = e.tvy;
+    t.vratio = 1.0;
+    if (!P.uniform_speed) t.vratio = P.airspeed / S.tvair[i];              // Q3
+    const int k = e.steps;                                                 // intruder moves after this step
+    if (MINSEP) {                                                          // game.py:237 (Q10: old traffic)
+        const double ox = (e.t0x + (double)(k - 1) * t.dx) - p.x, oy = (e.t0y + (double)(k - 1) * t.dy) - p.y;
+        e.minsep = fminf(e.minsep, sqrtf((float)(ox * ox + oy * oy)));
+    }
+    t.x = e.t0x + (double)k * t.dx;                                        // game.py:243-245
+    t.y = e.t0y + (double)k * t.dy;
+
+    // ---- game.observe / evaluate / is_done (game.py:194-314)
+    const int steps = k + 1;                                               // game.py:197
+    const PlayerView v = player_view(P, p, steps);
+    const Encounter en = encounter(P, p, t);
+    float r = shaped_reward(P, p, v, en, steps);
+    const bool coll = en.d2 < P.coll_d2;                                   // game.py:187 (strict, Q8)
+    const bool goal = v.dg2 < P.goal_r2;                                   // game.py:192
+    const bool tout = steps > P.max_steps;                                 // game.py:183
+    if (coll) r += P.reward_collision;                                     // game.py:279-284 (Q9)
+    if (goal) r += P.reward_goal;
+    const float ret = e.ret + r;                                           // game.py:287
+    const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
+                        : goal ? ACAS2D_OUTCOME_GOAL : 0;                  // game.py:297-310
+    const bool done = outcome != 0;
+
+    if (EMIT) {
+        ACAS_STCS(out.reward + i, r);
+        out.done[i] = (uint8_t)done;
+        if (out.flags) {
+            const bool oob = p.x < 0.0 || p.x > P.width || p.y < 0.0 || p.y > P.height;   // aircraft.py:28-29
+            out.flags[i] = (uint8_t)((coll ? ACAS2D_FLAG_COLLISION : 0) | (goal ? ACAS2D_FLAG_GOAL : 0) |
+                                     (tout ? ACAS2D_FLAG_TIMEOUT : 0) | (done ? ACAS2D_FLAG_DONE : 0) |
+                                     (oob ? ACAS2D_FLAG_OOB : 0));
+        }
+    } else if (reward_acc) {
+        *reward_acc += r;
+    }
+
+    if (!done || !P.auto_reset) {
+        if (EMIT) store_obs8(out.obs + 8 * i, v, en, P);
+        if (done) {   // reference ACAS2DEnv semantics: the finished game stays in place until reset()
+            if (EMIT) {
+                if (out.outcome) out.outcome[i] = (uint8_t)outcome;
+                if (out.ep_return) out.ep_return[i] = ret;
+                if (out.ep_length) out.ep_length[i] = steps;
+            }
+            tally_add(tally, outcome, steps, ret, e.minsep, MINSEP);
+        }
+        e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = steps; e.ret = ret;
+        return;
+    }
+
+    // ---- auto-reset (SB3 DummyVecEnv semantics)
+    if (EMIT) {
+        if (out.term_obs) store_obs8(out.term_obs + 8 * i, v, en, P);
+        if (out.outcome) out.outcome[i] = (uint8_t)outcome;
+        if (out.ep_return) out.ep_return[i] = ret;
+        if (out.ep_length) out.ep_length[i] = steps;
+    }
+    tally_add(tally, outcome, steps, ret, e.minsep, MINSEP);
+
+    const uint32_t episode = S.episode_idx[i];
+    S.episode_idx[i] = episode + 1u;
+    const Spawn0 sp = spawn_slot0(P, S.seed, S.gid0 + (uint64_t)i, episode);
+    p.x = P.player_x0; p.y = P.player_y0;
+    player_set_heading(P, p, sp.player_psi, 0.0);                          // a_lat = 0 in a new game
+    heading_to_velocity(P, sp.v, sp.psi, &t.dx, &t.dy);
+    t.x = sp.x; t.y = sp.y;
+    t.vratio = P.airspeed / sp.v;
+    S.tpsi[i] = sp.psi;
+    S.tvair[i] = sp.v;
+    const PlayerView v1 = player_view(P, p, 1);                            // environment.py:47: steps becomes 1
+    const Encounter e1 = encounter(P, p, t);
+    if (EMIT) store_obs8(out.obs + 8 * i, v1, e1, P);
+    e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = 1; e.ret = 0.0f;
+    e.t0x = t.x; e.t0y = t.y; e.tvx = t.dx; e.tvy = t.dy;
+    e.minsep = e1.d;                                                       // game.py:141
+    e.respawned = true;
+}
+
+ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
+{
+    const Vec2d pp = S.ppos[i];
+    const PlayerAux pa = S.paux[i];
+    const Vec2d t0 = S.tpos0[i];
+    const Vec2d tv = S.tvel[i];
+    e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.steps = pa.steps; e.ret = pa.ep_return;
+    e.t0x = t0.x; e.t0y = t0.y; e.tvx = tv.x; e.tvy = tv.y;
+    e.minsep = minsep ? S.min_sep[i] : 0.0f;
+    e.respawned = false;
+}
+
+ACAS_HD void store_env1(const StatePtrs &S, int64_t i, const Env1 &e, bool minsep)
+{
+    Vec2d pp; pp.x = e.px; pp.y = e.py;
+    PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps; pa.ep_return = e.ret;
+    S.ppos[i] = pp;
+    S.paux[i] = pa;
+    if (e.respawned) {
+        Vec2d t0; t0.x = e.t0x; t0.y = e.t0y;
+        Vec2d tv; tv.x = e.tvx; tv.y = e.tvy;
+        S.tpos0[i] = t0;
+        S.tvel[i] = tv;
+    }
+    if (minsep) S.min_sep[i] = e.minsep;
+}
+
+
+// ---------------------------------------------------------------- any N_TRAFFIC, one thread per env
+// Intruders streamed straight from global memory.  Correct for every N; it is the simple
+// form the shared-memory tiled kernel is checked against and the fallback for exotic N.
+template <bool MINSEP>
+ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, float action,
+                           const Sinks &out, Tally &tally)
+{
+    const int N = P.n_traffic;
+    const int L = 5 + 3 * N;
+    const Vec2d pp = S.ppos[i];
+    const PlayerAux pa = S.paux[i];
+    const double dpsi = (double)action * P.dpsi_per_action;
+    Player p;
+    p.x = pp.x; p.y = pp.y;
+    player_set_heading(P, p, wrap360(pa.psi + dpsi), dpsi);
+    player_advance(P, p);
+    const int k = pa.steps;
+    const int steps = k + 1;
+    const PlayerView v = player_view(P, p, steps);
+    float *row = out.obs + (int64_t)L * i;
+    float *trow = nullptr;
+    bool coll = false;
+    float minsep = MINSEP ? S.min_sep[i] : 0.0f;
+    Encounter e0;
+    for (int j = 0; j < N; ++j) {
+        const int64_t ij = i * N + j;
+        const Vec2d t0 = S.tpos0[ij], tv = S.tvel[ij];
+        Intruder t;
+        t.dx = tv.x; t.dy = tv.y;
+        t.vratio = P.uniform_speed ? 1.0 : P.airspeed / S.tvair[ij];
+        if (MINSEP) {
+            const double ox = (t0.x + (double)(k - 1) * t.dx) - p.x, oy = (t0.y + (double)(k - 1) * t.dy) - p.y;
+            minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
+        }
+        t.x = t0.x + (double)k * t.dx;
+        t.y = t0.y + (double)k * t.dy;
+        const Encounter en = encounter(P, p, t);
+        if (j == 0) e0 = en;
+        coll |= en.d2 < P.coll_d2;
+        row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
+        row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
+        row[5 + 3 * j + 2] = en.v_c * P.vc_scale;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) row[q] = v.obs[q];
+    float r = shaped_reward(P, p, v, e0, steps);
+    const bool goal = v.dg2 < P.goal_r2;
+    const bool tout = steps > P.max_steps;
+    if (coll) r += P.reward_collision;
+    if (goal) r += P.reward_goal;
+    float ret = pa.ep_return + r;
+    const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
+                        : goal ? ACAS2D_OUTCOME_GOAL : 0;
+    const bool done = outcome != 0;
+    out.reward[i] = r;
+    out.done[i] = (uint8_t)done;
+    if (out.flags) {
+        const bool oob = p.x < 0.0 || p.x > P.width || p.y < 0.0 || p.y > P.height;
+        out.flags[i] = (uint8_t)((coll ? ACAS2D_FLAG_COLLISION : 0) | (goal ? ACAS2D_FLAG_GOAL : 0) |
+                                 (tout ? ACAS2D_FLAG_TIMEOUT : 0) | (done ? ACAS2D_FLAG_DONE : 0) |
+                                 (oob ? ACAS2D_FLAG_OOB : 0));
+    }
+    int steps_out = steps;
+    if (done) {
+        if (out.outcome) out.outcome[i] = (uint8_t)outcome;
+        if (out.ep_return) out.ep_return[i] = ret;
+        if (out.ep_length) out.ep_length[i] = steps;
+        tally_add(tally, outcome, steps, ret, minsep, MINSEP);
+        if (P.auto_reset) {
+            if (out.term_obs) {
+                trow = out.term_obs + (int64_t)L * i;
+                for (int q = 0; q < L; ++q) trow[q] = row[q];
+            }
+            const uint32_t episode = S.episode_idx[i];
+            S.episode_idx[i] = episode + 1u;
+            const uint64_t gid = S.gid0 + (uint64_t)i;
+            const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
+            p.x = P.player_x0; p.y = P.player_y0;
+            player_set_heading(P, p, sp.player_psi, 0.0);
+            const PlayerView v1 = player_view(P, p, 1);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) row[q] = v1.obs[q];
+            minsep = INFINITY;
+            for (int j = 0; j < N; ++j) {
+                const int64_t ij = i * N + j;
+                SpawnN sn;
+                if (j == 0) { sn.x = sp.x; sn.y = sp.y; sn.v = sp.v; sn.psi = sp.psi; }
+                else sn = spawn_slot(P, S.seed, gid, episode, (uint32_t)j);
+                Intruder t;
+                heading_to_velocity(P, sn.v, sn.psi, &t.dx, &t.dy);
+                t.x = sn.x; t.y = sn.y;
+                t.vratio = P.airspeed / sn.v;
+                Vec2d a; a.x = t.x; a.y = t.y;
+                Vec2d b; b.x = t.dx; b.y = t.dy;
+                S.tpos0[ij] = a; S.tvel[ij] = b; S.tpsi[ij] = sn.psi; S.tvair[ij] = sn.v;
+                const Encounter en = encounter(P, p, t);
+                minsep = fminf(minsep, en.d);
+                row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
+                row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
+                row[5 + 3 * j + 2] = en.v_c * P.vc_scale;
+            }
+            steps_out = 1;
+            ret = 0.0f;
+        }
+    }
+    Vec2d np; np.x = p.x; np.y = p.y;
+    PlayerAux na; na.psi = p.psi; na.steps = steps_out; na.ep_return = ret;
+    S.ppos[i] = np;
+    S.paux[i] = na;
+    if (MINSEP) S.min_sep[i] = minsep;
+}
+
+// ---------------------------------------------------------------- reset / inject / extract
+// ACAS2DEnv.reset(): new game (game.py:27-160) + observe (game.py:194-220).
+ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float *obs)
+{
+    const int N = P.n_traffic;
+    const int L = 5 + 3 * N;
+    const uint32_t episode = S.episode_idx[i];
+    S.episode_idx[i] = episode + 1u;
+    const uint64_t gid = S.gid0 + (uint64_t)i;
+    const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
+    Player p;
+    p.x = P.player_x0; p.y = P.player_y0;
+    player_set_heading(P, p, sp.player_psi, 0.0);
+    const PlayerView v = player_view(P, p, 1);
+    float *row = obs ? obs + (int64_t)L * i : nullptr;
+    if (row) for (int q = 0; q < 5; ++q) row[q] = v.obs[q];
+    float minsep = INFINITY;
+    for (int j = 0; j < N; ++j) {
+        const int64_t ij = i * N + j;
+        SpawnN sn;
+        if (j == 0) { sn.x = sp.x; sn.y = sp.y; sn.v = sp.v; sn.psi = sp.psi; }
+        else sn = spawn_slot(P, S.seed, gid, episode, (uint32_t)j);
+        Intruder t;
+        heading_to_velocity(P, sn.v, sn.psi, &t.dx, &t.dy);
+        t.x = sn.x; t.y = sn.y;
+        t.vratio = P.airspeed / sn.v;
+        Vec2d a; a.x = t.x; a.y = t.y;
+        Vec2d b; b.x = t.dx; b.y = t.dy;
+        S.tpos0[ij] = a; S.tvel[ij] = b; S.tpsi[ij] = sn.psi; S.tvair[ij] = sn.v;
+        const Encounter en = encounter(P, p, t);
+        minsep = fminf(minsep, en.d);
+        if (row) {
+            row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
+            row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
+            row[5 + 3 * j + 2] = en.v_c * P.vc_scale;
+        }
+    }
+    Vec2d np; np.x = p.x; np.y = p.y;
+    PlayerAux na; na.psi = p.psi; na.steps = 1; na.ep_return = 0.0f;
+    S.ppos[i] = np;
+    S.paux[i] = na;
+    if (S.min_sep) S.min_sep[i] = minsep;
+}
+
+ACAS_HD void inject_env(const DevParams &P, const StatePtrs &S, int64_t i, const double *player,
+                        const double *traffic, const int32_t *steps, const double *total_reward)
+{
+    const int N = P.n_traffic;
+    Vec2d np; np.x = player[3 * i]; np.y = player[3 * i + 1];
+    PlayerAux na; na.psi = player[3 * i + 2]; na.steps = steps[i]; na.ep_return = (float)total_reward[i];
+    S.ppos[i] = np;
+    S.paux[i] = na;
+    float minsep = INFINITY;
+    const double back = (double)(na.steps - 1);
+    for (int j = 0; j < N; ++j) {
+        const int64_t ij = i * N + j;
+        const double x = traffic[4 * ij], y = traffic[4 * ij + 1], v = traffic[4 * ij + 2], psi = traffic[4 * ij + 3];
+        Vec2d b;
+        heading_to_velocity(P, v, psi, &b.x, &b.y);
+        Vec2d a; a.x = x - back * b.x; a.y = y - back * b.y;       // closed-form origin (steps == 1)
+        S.tpos0[ij] = a; S.tvel[ij] = b; S.tpsi[ij] = psi; S.tvair[ij] = v;
+        const double ox = x - np.x, oy = y - np.y;
+        minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
+    }
+    if (S.min_sep) S.min_sep[i] = minsep;
+}
+
+ACAS_HD void extract_env(const DevParams &P, const StatePtrs &S, int64_t i, double *player, double *traffic,
+                         int32_t *steps, double *total_reward)
+{
+    const int N = P.n_traffic;
+    const Vec2d pp = S.ppos[i];
+    const PlayerAux pa = S.paux[i];
+    if (player) { player[3 * i] = pp.x; player[3 * i + 1] = pp.y; player[3 * i + 2] = pa.psi; }
+    if (steps) steps[i] = pa.steps;
+    if (total_reward) total_reward[i] = (double)pa.ep_return;
+    if (traffic) {
+        const double k = (double)(pa.steps - 1);
+        for (int j = 0; j < N; ++j) {
+            const int64_t ij = i * N + j;
+            const Vec2d a = S.tpos0[ij], b = S.tvel[ij];
+            traffic[4 * ij + 0] = a.x + k * b.x;
+            traffic[4 * ij + 1] = a.y + k * b.y;
+            traffic[4 * ij + 2] = S.tvair[ij];
+            traffic[4 * ij + 3] = S.tpsi[ij];
+        }
+    }
+}
+
+}  // namespace acas2d

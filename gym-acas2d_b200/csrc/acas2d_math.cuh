@@ -1,0 +1,311 @@
+// acas2d_math.cuh -- per-environment arithmetic of the ACAS-2D step, written once and
+// inlined into every kernel of acas2d_kernels.cu.
+//
+// Precision plan (DESIGN.md "Numerics"):
+//   * the FLAG CHAIN is float64: heading, sin/cos of the heading, player position,
+//     intruder position, squared separations and the goal / collision / timeout tests.
+//     The reference is float64 Python (aircraft.py:16-26, game.py:182-192); keeping this
+//     chain in float64 keeps collision / goal / done flags bit-exact against it.
+//   * sign-deciding products (closing-speed dot product, relative-velocity cross product
+//     and its x component, Q4/Q12) are formed in float64 from float64 differences, then
+//     rounded once to float32.
+//   * everything that is only ever emitted as a float32 observation or reward (square
+//     roots, atan2, normalisation, reward shaping) is float32.
+//
+// The functions are __host__ __device__ so tests/hostcheck can compile the very same
+// source with g++ and compare it with the CPU oracle without a GPU.  That host build is
+// test infrastructure; the product never runs it.
+//
+// Reference citations: aircraft.py / kinematics.py / rewards.py / game.py =
+// gym_ACAS2D/envs/<file>; settings.py = gym_ACAS2D/settings.py.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ACAS_HD __host__ __device__ __forceinline__
+#else
+#define ACAS_HD static inline
+#endif
+
+namespace acas2d {
+
+struct alignas(16) Vec2d { double x, y; };
+
+// 16-byte per-env record: heading [deg], game.steps, game.total_reward so far.
+struct alignas(16) PlayerAux { double psi; int32_t steps; float ep_return; };
+
+// Launch-time constants, derived on the host from acas2d_params (see make_dev_params).
+struct DevParams {
+    // ---- float64 flag chain
+    double v_dt;            // AIRSPEED / FPS: player displacement per step (aircraft.py:25-26)
+    double dpsi_per_action; // ACC_LAT_LIMIT / AIRSPEED: heading change [deg] per unit action (Q1)
+    double lookahead_rad;   // (1/FPS) * pi/180: closing_speed's look-ahead turn per degree of dpsi (Q2)
+    double goal_x, goal_y;  // game.py:80-81
+    double coll_d2;         // (2*COLLISION_RADIUS)^2, game.py:187
+    double goal_r2;         // GOAL_RADIUS^2, game.py:192
+    double width, height;   // aircraft.py:28-29
+    double inv_360;         // obs[1] = psi/360, game.py:200
+    double inv_d_dev_max;   // obs[2] = d_dev/d_dev_max, game.py:201
+    // ---- spawn (game.py:85-116)
+    double dt, airspeed;
+    double player_x0, player_y0, player_psi_base, player_heading_lim;
+    double traffic_heading_lim, factor_min, factor_span;
+    double t0_x, t0_y_up, t0_y_span;   // intruder 0: (WIDTH-CR, CR + starts_down*(HEIGHT-2CR))
+    double tn_x_span, tn_y_span;       // intruders n>0: U(0, WIDTH-SIZE) x U(0, 3*HEIGHT/5)
+    // ---- float32 observation / reward block
+    float inv_max_steps;    // obs[0], time discount (game.py:199,262)
+    float inv_d_goal_max;   // obs[3], game.py:202
+    float inv_d_sep_max;    // game.py:208
+    float inv_d_cpa_max;    // game.py:209
+    float vc_scale;         // FPS / v_closing_max: displacement-per-step units -> obs (game.py:210)
+    float fps;
+    float inv_safe_distance;   // rewards.py:16
+    float rw_dev_max;          // 704 at defaults, rewards.py:22-23
+    float inv_rw_dev_max;
+    float inv_rw_goal_max;     // 1/3408 at defaults, rewards.py:46-47
+    float reward_goal, reward_collision;
+    // ---- integers
+    int32_t n_traffic, max_steps, auto_reset, uniform_speed;
+};
+
+static constexpr double kDeg2Rad = 0.017453292519943295;  // pi/180
+static constexpr float kTwoPiF = 6.283185307179586f;
+static constexpr float kInvTwoPiF = 0.15915494309189535f;
+
+ACAS_HD float acas_rsqrtf(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+ACAS_HD void acas_sincos(double x, double *s, double *c)
+{
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// Python float `%` with divisor 360 (aircraft.py:22, kinematics.py:58,68, game.py:92,106):
+// result in [0, 360], equal to 360.0 only when a tiny negative value rounds up.
+ACAS_HD double wrap360(double t)
+{
+    if (t >= 0.0) {
+        if (t < 360.0) return t;
+        if (t < 720.0) return t - 360.0;      // exact, == fmod
+    } else if (t >= -360.0) {
+        return t + 360.0;                      // fmod(t,360) == t, then + 360
+    }
+    double r = fmod(t, 360.0);
+    if (r != 0.0) { if (r < 0.0) r += 360.0; } else { r = 0.0; }
+    return r;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+struct U4 { uint32_t x, y, z, w; };
+
+ACAS_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+ACAS_HD double u01(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
+
+// Action stream of the synthetic rollout: a ~ U(-1,1), float32, one Philox block per
+// (global env id, step index); word 0 is used.
+ACAS_HD float random_action(uint64_t action_seed, uint64_t gid, uint64_t step_index)
+{
+    U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step_index,
+                         (uint32_t)(step_index >> 32) ^ 0xAC7105EDu,
+                         (uint32_t)action_seed, (uint32_t)(action_seed >> 32));
+    return (float)(2.0 * u01(r.x) - 1.0);
+}
+
+// ------------------------------------------------------------------ state in registers
+struct Player {
+    double x, y, psi;   // position [px], heading [deg]
+    double c, s;        // cos / sin of the heading
+    double cl, sl;      // cos / sin of closing_speed's look-ahead heading (Q2)
+};
+
+struct Intruder {
+    double x, y;        // CURRENT position
+    double dx, dy;      // displacement per step (v cos psi dt, v sin psi dt)
+    double vratio;      // player speed / intruder speed (Q3; 1 when speeds are uniform)
+};
+
+// aircraft.py:16-26 for the player: heading += a_lat/v degrees (Q1), wrap, move one step.
+// dpsi is the heading increment in degrees.  Also prepares the look-ahead heading of
+// kinematics.py:57-60 (psi + dpsi*dt), a tiny rotation of the new heading.
+ACAS_HD void player_set_heading(const DevParams &P, Player &p, double psi, double dpsi)
+{
+    p.psi = psi;
+    acas_sincos(psi * kDeg2Rad, &p.s, &p.c);
+    const double d = dpsi * P.lookahead_rad;             // radians, |d| <= 1.7e-4 for |action| <= 1
+    double sd, cd;
+    if (fabs(d) < 0.0078125) {                           // Taylor: error < 4e-16
+        const double d2 = d * d;
+        sd = d * (1.0 + d2 * (-1.0 / 6.0 + d2 * (1.0 / 120.0)));
+        cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24.0 + d2 * (-1.0 / 720.0)));
+    } else {                                             // unclipped actions (Q19)
+        acas_sincos(d, &sd, &cd);
+    }
+    p.cl = p.c * cd - p.s * sd;
+    p.sl = p.s * cd + p.c * sd;
+}
+
+ACAS_HD void player_advance(const DevParams &P, Player &p)
+{
+    p.x = p.x + p.c * P.v_dt;
+    p.y = p.y + p.s * P.v_dt;
+}
+
+// Per-intruder quantities of game.py:205-210: separation, signed distance of closest
+// approach (kinematics.py:40-49) and closing speed (kinematics.py:52-79).
+struct Encounter {
+    double d2;      // squared separation (float64: collision test)
+    float d;        // separation
+    float d_cpa;    // signed, px
+    float v_c;      // px per STEP * FPS is applied by the caller through vc_scale / fps
+};
+
+ACAS_HD Encounter encounter(const DevParams &P, const Player &p, const Intruder &t)
+{
+    Encounter e;
+    const double rx = t.x - p.x, ry = t.y - p.y;          // bearing vector player -> intruder
+    e.d2 = rx * rx + ry * ry;
+    // relative displacement per step at the CURRENT headings (kinematics.py:25-37, times dt)
+    const double wx = p.c * P.v_dt - t.dx, wy = p.s * P.v_dt - t.dy;
+    const double w2 = wx * wx + wy * wy;
+    // d*sin(a_rel - arctan(wy/wx)) == sign(wx) * (ry*wx - rx*wy) / |w|   (Q12 keeps cos(h) >= 0)
+    const double cross = ry * wx - rx * wy;
+    // one-step look-ahead (kinematics.py:57-77): p' - t' and u' - u_t' with Q3 on the y term
+    const double ex = p.cl * P.v_dt - t.dx;
+    const double qx = ex - rx;
+    const double qy = (p.sl * P.v_dt - t.dy) - ry;
+    const double ey = p.sl * P.v_dt - t.dy * t.vratio;
+    const double q2 = qx * qx + qy * qy;
+    const double dot = ex * qx + ey * qy;
+
+    e.d = sqrtf((float)e.d2);
+    const float cr = (float)cross * acas_rsqrtf((float)w2);
+    e.d_cpa = (wx < 0.0) ? -cr : cr;
+    e.v_c = (float)dot * acas_rsqrtf((float)q2);          // displacement units; * FPS = px/s (Q4)
+    return e;
+}
+
+// Player-only observation terms and the shaped reward (game.py:199-203,249-263,
+// rewards.py:5-60).  `steps` is the already incremented counter (Q5, Q6).
+struct PlayerView {
+    float obs[5];
+    double dg2;     // squared goal distance (float64: goal test)
+    float d_goal, phi_deg, d_dev;
+};
+
+ACAS_HD PlayerView player_view(const DevParams &P, const Player &p, int32_t steps)
+{
+    PlayerView v;
+    const double gx = P.goal_x - p.x, gy = P.goal_y - p.y;
+    v.dg2 = gx * gx + gy * gy;
+    v.d_goal = sqrtf((float)v.dg2);
+    // heading_to_goal (game.py:171-173, kinematics.py:16-22): degrees(atan2 mod 2pi)
+    float phi = atan2f((float)gy, (float)gx);
+    if (phi < 0.0f) phi += kTwoPiF;
+    const float phi_turns = phi * kInvTwoPiF;
+    v.phi_deg = phi_turns * 360.0f;
+    // plan_deviation (game.py:175-180) = d_goal*sin(heading_to_goal) == goal_y - y
+    v.d_dev = (float)gy;
+    v.obs[0] = (float)steps * P.inv_max_steps;
+    v.obs[1] = (float)(p.psi * P.inv_360);
+    v.obs[2] = (float)(gy * P.inv_d_dev_max);
+    v.obs[3] = v.d_goal * P.inv_d_goal_max;
+    v.obs[4] = phi_turns;
+    return v;
+}
+
+// step_reward_5 (rewards.py:53-60) with intruder 0 only (Q7), times the time discount (Q6).
+ACAS_HD float shaped_reward(const DevParams &P, const Player &p, const PlayerView &v,
+                            const Encounter &e0, int32_t steps)
+{
+    // delta_heading (kinematics.py:82-83); psi - phi formed in float64 before rounding
+    const float a = fabsf((float)(p.psi - (double)v.phi_deg));
+    const float dh = fminf(a, 360.0f - a);
+    float h = 1.0f - dh * (1.0f / 180.0f);
+    h = h * h; h = h * h;                                   // rewards.py:7
+    float r;
+    if (e0.v_c <= 0.0f) {                                    // rewards.py:54 (NaN -> else, as in Python)
+        float c = e0.d_cpa * P.inv_safe_distance;            // rewards.py:16
+        c = c * c; c = c * c;
+        c = fminf(1.0f, c);                                  // min(1, nan) == 1 in Python, fminf agrees
+        const float ad = fabsf(v.d_dev);                     // rewards.py:21-27
+        const float dv = (ad > P.rw_dev_max) ? 0.0f : sqrtf(fmaxf(0.0f, 1.0f - ad * P.inv_rw_dev_max));
+        r = h * c * dv;
+    } else {
+        float g = 1.0f - v.d_goal * P.inv_rw_goal_max;       // rewards.py:48
+        g = g * g; g = g * g;
+        r = h * fminf(1.0f, g);
+    }
+    return r * (1.0f - (float)steps * P.inv_max_steps);      // game.py:262-263
+}
+
+// ------------------------------------------------------------------ spawn (game.py:85-116)
+// Draw slot 0: player heading jitter, starts_down, intruder-0 speed factor, intruder-0 heading jitter.
+struct Spawn0 { double player_psi; double x, y, v, psi; };
+
+ACAS_HD Spawn0 spawn_slot0(const DevParams &P, uint64_t seed, uint64_t gid, uint32_t episode)
+{
+    const U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), episode, 0u,
+                               (uint32_t)seed, (uint32_t)(seed >> 32));
+    Spawn0 o;
+    const double hl = P.player_heading_lim, tl = P.traffic_heading_lim;
+    o.player_psi = wrap360(P.player_psi_base + (-hl + (2.0 * hl) * u01(r.x)));    // game.py:91-92
+    const double sd = (double)(r.y >> 31);                                          // game.py:98
+    o.x = P.t0_x;                                                                    // game.py:100
+    o.y = P.t0_y_up + sd * P.t0_y_span;                                              // game.py:101
+    o.v = (P.factor_min + P.factor_span * u01(r.z)) * P.airspeed;                    // game.py:103
+    o.psi = wrap360((145.0 + sd * 70.0) + (-tl + (2.0 * tl) * u01(r.w)));            // game.py:105-106
+    return o;
+}
+
+// Draw slot i >= 1: intruder i position, speed factor, heading (game.py:109-114).
+struct SpawnN { double x, y, v, psi; };
+
+ACAS_HD SpawnN spawn_slot(const DevParams &P, uint64_t seed, uint64_t gid, uint32_t episode, uint32_t i)
+{
+    const U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), episode, i,
+                               (uint32_t)seed, (uint32_t)(seed >> 32));
+    SpawnN o;
+    o.x = P.tn_x_span * u01(r.x);
+    o.y = P.tn_y_span * u01(r.y);
+    o.v = (P.factor_min + P.factor_span * u01(r.z)) * P.airspeed;
+    o.psi = 360.0 * u01(r.w);
+    return o;
+}
+
+// Per-step displacement of an aircraft flying straight (aircraft.py:23-26 with a_lat = 0).
+ACAS_HD void heading_to_velocity(const DevParams &P, double v, double psi, double *dx, double *dy)
+{
+    double s, c;
+    acas_sincos(psi * kDeg2Rad, &s, &c);
+    *dx = (v * c) * P.dt;
+    *dy = (v * s) * P.dt;
+}
+
+}  // namespace acas2d

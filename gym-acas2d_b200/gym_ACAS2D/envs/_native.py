@@ -1,0 +1,167 @@
+"""ctypes binding of ``libacas2d_b200.so`` (C ABI: ``include/acas2d_b200.h``).
+
+The library is built in-tree by ``build()`` (``nvcc -gencode arch=compute_100a,code=sm_100a``)
+and loaded from ``gym-acas2d_b200/csrc``.  There is no fallback: if the library is missing
+or the machine has no CUDA device, the environment constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from typing import Optional
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # gym-acas2d_b200/
+CSRC_DIR = os.path.join(_PKG_ROOT, "csrc")
+REPO_ROOT = os.path.dirname(_PKG_ROOT)
+LIB_PATH = os.path.join(CSRC_DIR, "libacas2d_b200.so")
+SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+ABI_VERSION = 1
+MAX_TRAFFIC = 1024
+STAT_SLOTS, STAT_FIELDS = 128, 16
+STAT_NAMES = ("episodes", "goal", "collision", "timeout", "length_sum", "return_fx", "min_sep_fx")
+STAT_FX_SCALE = 1048576.0
+FLAG_COLLISION, FLAG_GOAL, FLAG_TIMEOUT, FLAG_DONE, FLAG_OOB = 1, 2, 4, 8, 16
+
+EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
+           "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
+           "acas2d_launch_count")
+
+ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
+
+
+class Params(ctypes.Structure):
+    """``acas2d_params`` (include/acas2d_b200.h)."""
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "width", "height", "fps", "max_steps", "aircraft_size", "collision_radius", "goal_radius",
+        "safe_distance", "airspeed", "airspeed_factor_min", "airspeed_factor_max", "acc_lat_limit",
+        "player_heading_lim", "traffic_heading_lim", "reward_goal", "reward_collision",
+        "goal_x", "goal_y", "player_x0", "player_y0", "player_psi_base",
+        "d_goal_max", "d_dev_max", "d_separation_max", "d_cpa_max", "v_closing_max")] + [
+        ("n_traffic", ctypes.c_int32), ("auto_reset", ctypes.c_int32)]
+
+
+class State(ctypes.Structure):
+    """``acas2d_state``: device pointers owned by the caller."""
+    _fields_ = [("num_envs", ctypes.c_int64),
+                ("ppos", ctypes.c_void_p), ("paux", ctypes.c_void_p),
+                ("tpos0", ctypes.c_void_p), ("tvel", ctypes.c_void_p),
+                ("tpsi", ctypes.c_void_p), ("tvair", ctypes.c_void_p),
+                ("episode_idx", ctypes.c_void_p), ("min_sep", ctypes.c_void_p),
+                ("stats", ctypes.c_void_p),
+                ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_uint64)]
+
+
+class StepAux(ctypes.Structure):
+    """``acas2d_step_aux``: optional per-step outputs."""
+    _fields_ = [("flags", ctypes.c_void_p), ("outcome", ctypes.c_void_p), ("term_obs", ctypes.c_void_p),
+                ("ep_return", ctypes.c_void_p), ("ep_length", ctypes.c_void_p)]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a in-tree (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC_DIR, s) for s in SOURCES] + [os.path.join(REPO_ROOT, "include", "acas2d_b200.h")]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-o", LIB_PATH, os.path.join(CSRC_DIR, "acas2d_kernels.cu")]
+        subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
+    """Attach argument / result types to every exported entry point."""
+    vp, PP, SP, AP = ctypes.c_void_p, ctypes.POINTER(Params), ctypes.POINTER(State), ctypes.POINTER(StepAux)
+    lib.acas2d_abi_version.argtypes = []
+    lib.acas2d_params_default.argtypes = [PP, ctypes.c_int32]
+    lib.acas2d_reset.argtypes = [PP, SP, vp, vp, vp]
+    lib.acas2d_step.argtypes = [PP, SP, vp, vp, vp, vp, AP, vp]
+    lib.acas2d_step_host.argtypes = [PP, SP, vp, vp, vp, vp, vp, vp, vp, vp, AP, vp]
+    lib.acas2d_inject_state.argtypes = [PP, SP, vp, vp, vp, vp, vp]
+    lib.acas2d_extract_state.argtypes = [PP, SP, vp, vp, vp, vp, vp]
+    lib.acas2d_rollout_random.argtypes = [PP, SP, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
+    lib.acas2d_random_actions.argtypes = [SP, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
+    lib.acas2d_launch_count.argtypes = []
+    lib.acas2d_launch_count.restype = ctypes.c_int64
+    return lib
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  The ACAS-2D batched step has no CPU fallback.")
+        lib = declare(ctypes.CDLL(LIB_PATH))
+        if lib.acas2d_abi_version() != ABI_VERSION:
+            raise RuntimeError("libacas2d_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    if code < 0:
+        raise ValueError(f"{what}: {ERRORS.get(code, 'error')} (code {code})")
+    raise RuntimeError(f"{what}: CUDA error {code}")
+
+
+def params_from_settings(settings=None, n_traffic: Optional[int] = None, auto_reset: bool = False, **overrides) -> Params:
+    """Build ``acas2d_params`` from a settings module / mapping (reference game.py:80-128)."""
+    if settings is None:
+        from gym_ACAS2D import settings as settings_mod
+        settings = settings_mod
+    get = (lambda k: overrides[k] if k in overrides else
+           (settings[k] if isinstance(settings, dict) else getattr(settings, k)))
+    lo, hi = int(get("MIN_TRAFFIC")), int(get("MAX_TRAFFIC"))
+    if n_traffic is None:
+        if lo != hi:
+            raise NotImplementedError(
+                "MIN_TRAFFIC != MAX_TRAFFIC: the reference pads the observation by 2 per missing intruder "
+                "(game.py:213) and breaks its own Box shape; only a fixed traffic count is supported")
+        n_traffic = hi
+    n_traffic = int(n_traffic)
+    if n_traffic < 1:
+        raise ValueError("the reference requires at least one intruder (game.py:146-147,254-255)")
+    if n_traffic > MAX_TRAFFIC:
+        raise ValueError(f"n_traffic > {MAX_TRAFFIC} is not supported")
+    p = Params()
+    p.width, p.height, p.fps = float(get("WIDTH")), float(get("HEIGHT")), float(get("FPS"))
+    p.max_steps = float(get("MAX_STEPS"))
+    p.aircraft_size = float(get("AIRCRAFT_SIZE"))
+    p.collision_radius = float(get("COLLISION_RADIUS"))
+    p.goal_radius = float(get("GOAL_RADIUS"))
+    p.safe_distance = float(get("SAFE_DISTANCE"))
+    p.airspeed = float(get("AIRSPEED"))
+    p.airspeed_factor_min = float(get("AIRSPEED_FACTOR_MIN"))
+    p.airspeed_factor_max = float(get("AIRSPEED_FACTOR_MAX"))
+    p.acc_lat_limit = float(get("ACC_LAT_LIMIT"))
+    p.player_heading_lim = float(get("PLAYER_INITIAL_HEADING_LIM"))
+    p.traffic_heading_lim = float(get("TRAFFIC_INITIAL_HEADING_LIM"))
+    p.reward_goal, p.reward_collision = float(get("REWARD_GOAL")), float(get("REWARD_COLLISION"))
+    p.goal_x = p.width - p.goal_radius                          # game.py:80
+    p.goal_y = p.height / 2                                     # game.py:81
+    p.player_x0 = p.collision_radius                            # game.py:85
+    p.player_y0 = p.height / 2                                  # game.py:86
+    p.player_psi_base = math.degrees(math.atan2(p.goal_y - p.player_y0, p.goal_x - p.player_x0) % (2 * math.pi))
+    reach = (p.airspeed / p.fps) * p.max_steps
+    p.d_goal_max = math.hypot(p.player_x0 - p.goal_x, p.player_y0 - p.goal_y) + reach     # game.py:120
+    p.d_dev_max = reach                                         # game.py:122
+    diag = math.sqrt(p.width ** 2 + p.height ** 2)
+    p.d_separation_max = diag + 2 * reach                       # game.py:124
+    p.d_cpa_max = diag                                          # game.py:126
+    p.v_closing_max = 2 * (p.airspeed_factor_max * p.airspeed)  # game.py:128
+    p.n_traffic = n_traffic
+    p.auto_reset = 1 if auto_reset else 0
+    return p

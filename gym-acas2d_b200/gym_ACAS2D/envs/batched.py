@@ -1,0 +1,283 @@
+"""``BatchedACAS2D`` -- B independent ACAS-2D games stepped by one CUDA kernel per call.
+
+This is the vectorised surface the north star adds next to the reference's single-env
+API: ``step(actions[B]) -> (obs[B, 5+3N], reward[B], done[B])`` on device tensors, with the
+semantics of ``ACAS2DEnv.step`` (reference gym_ACAS2D/envs/environment.py:29-42) applied to
+every env, and of ``ACAS2DEnv.reset`` (environment.py:44-48) on reset / auto-reset.
+
+PyTorch is used for what it is good at here -- device memory, streams, CUDA graphs and
+``torch.distributed`` -- and nothing else: all arithmetic happens in
+``csrc/acas2d_kernels.cu`` behind the C ABI of ``include/acas2d_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import Params, State, StepAux
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("BatchedACAS2D needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"BatchedACAS2D runs on CUDA devices only, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class BatchedACAS2D:
+    """SoA state of ``num_envs`` games in HBM + the kernels that advance it.
+
+    Parameters
+    ----------
+    num_envs       B, envs owned by this process / GPU.
+    n_traffic      intruders per env (default: ``settings.MAX_TRAFFIC``).
+    seed           Philox key for spawns (default ``settings.RANDOM_SEED``).
+    env_id_offset  global id of local env 0; spawns depend on the global id only, so a batch
+                   sharded over R ranks reproduces the single-GPU batch exactly.
+    auto_reset     True: SB3 VecEnv semantics (finished envs respawn inside ``step`` and the
+                   returned obs row is the reset observation).  False: reference ``ACAS2DEnv``
+                   semantics (a finished game stays in place until ``reset``).
+    track_min_sep  keep the per-episode minimum separation (reference ``d_sep_record``,
+                   game.py:237); costs 8 B/env-step of extra HBM traffic.
+    """
+
+    def __init__(self, num_envs: int, n_traffic: Optional[int] = None, device="cuda", seed: Optional[int] = None,
+                 env_id_offset: int = 0, auto_reset: bool = True, track_min_sep: bool = False,
+                 settings=None, **setting_overrides):
+        self.lib = _native.load()
+        self.device = _require_cuda(device)
+        self.params: Params = _native.params_from_settings(settings, n_traffic, auto_reset, **setting_overrides)
+        if seed is None:
+            from gym_ACAS2D.settings import RANDOM_SEED
+            seed = RANDOM_SEED
+        self.num_envs = B = int(num_envs)
+        self.n_traffic = N = int(self.params.n_traffic)
+        self.obs_dim = L = 5 + 3 * N
+        self.seed, self.env_id_offset = int(seed), int(env_id_offset)
+        self.auto_reset = bool(auto_reset)
+        dev, f64, f32 = self.device, torch.float64, torch.float32
+        with torch.cuda.device(dev):
+            # ---- state (layout: include/acas2d_b200.h)
+            self.ppos = torch.zeros(B, 2, dtype=f64, device=dev)
+            self.paux = torch.zeros(B, 2, dtype=f64, device=dev)          # 16 B records {psi, steps, ep_return}
+            self.tpos0 = torch.zeros(B, N, 2, dtype=f64, device=dev)
+            self.tvel = torch.zeros(B, N, 2, dtype=f64, device=dev)
+            self.tpsi = torch.zeros(B, N, dtype=f64, device=dev)
+            self.tvair = torch.ones(B, N, dtype=f64, device=dev)
+            self.episode_idx = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.min_sep = torch.zeros(B, dtype=f32, device=dev) if track_min_sep else None
+            self.stats = torch.zeros(_native.STAT_SLOTS, _native.STAT_FIELDS, dtype=torch.int64, device=dev)
+            # ---- per-step outputs (overwritten by every step)
+            self.obs = torch.zeros(B, L, dtype=f32, device=dev)
+            self.reward = torch.zeros(B, dtype=f32, device=dev)
+            self.done_u8 = torch.zeros(B, dtype=torch.uint8, device=dev)
+            self.flags = torch.zeros(B, dtype=torch.uint8, device=dev)
+            self.outcome = torch.zeros(B, dtype=torch.uint8, device=dev)
+            self.term_obs = torch.zeros(B, L, dtype=f32, device=dev)
+            self.ep_return = torch.zeros(B, dtype=f32, device=dev)
+            self.ep_length = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._state = State(
+            num_envs=B, ppos=self.ppos.data_ptr(), paux=self.paux.data_ptr(), tpos0=self.tpos0.data_ptr(),
+            tvel=self.tvel.data_ptr(), tpsi=self.tpsi.data_ptr(), tvair=self.tvair.data_ptr(),
+            episode_idx=self.episode_idx.data_ptr(),
+            min_sep=self.min_sep.data_ptr() if track_min_sep else None,
+            stats=self.stats.data_ptr(), seed=self.seed, env_id_offset=self.env_id_offset)
+        self._aux_full = StepAux(flags=self.flags.data_ptr(), outcome=self.outcome.data_ptr(),
+                                 term_obs=self.term_obs.data_ptr(), ep_return=self.ep_return.data_ptr(),
+                                 ep_length=self.ep_length.data_ptr())
+        self._aux_lean = StepAux(flags=None, outcome=self.outcome.data_ptr(), term_obs=None,
+                                 ep_return=self.ep_return.data_ptr(), ep_length=self.ep_length.data_ptr())
+        self._host = None          # pinned staging buffers of step_host
+        self._actions_dev = torch.zeros(B, dtype=f32, device=dev)
+        self.launches = 0          # kernels launched through this object
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _p(self):
+        return ctypes.byref(self.params)
+
+    def _s(self):
+        return ctypes.byref(self._state)
+
+    @property
+    def done(self) -> torch.Tensor:
+        return self.done_u8.view(torch.bool)
+
+    def _as_actions(self, actions) -> torch.Tensor:
+        a = actions
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a), device=self.device)
+        if a.device != self.device or a.dtype != torch.float32:
+            a = a.to(device=self.device, dtype=torch.float32)
+        a = a.reshape(-1)
+        if a.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {a.numel()}")
+        return a.contiguous()
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """New game for every env (or those with ``mask`` set); returns the obs buffer [B, L]."""
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_reset(self._p(), self._s(), mptr, self.obs.data_ptr(), self._stream()),
+                          "acas2d_reset")
+        self.launches += 1
+        return self.obs
+
+    def step(self, actions, full_outputs: bool = True):
+        """One environment step for all envs.  Returns views of the internal (obs, reward, done)
+        buffers; they are overwritten by the next call.  With ``full_outputs`` the per-env
+        ``flags`` and ``term_obs`` buffers are also written (``outcome`` / ``ep_return`` /
+        ``ep_length`` always are, where done)."""
+        a = self._as_actions(actions)
+        aux = self._aux_full if full_outputs else self._aux_lean
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_step(self._p(), self._s(), a.data_ptr(), self.obs.data_ptr(),
+                                               self.reward.data_ptr(), self.done_u8.data_ptr(),
+                                               ctypes.byref(aux), self._stream()), "acas2d_step")
+        self.launches += 1
+        return self.obs, self.reward, self.done
+
+    def step_host(self, actions: np.ndarray):
+        """Host-buffer step (the end-to-end path): ``actions`` float32[B] in host memory ->
+        (obs float32[B, L], reward float32[B], done bool[B]) numpy views of pinned buffers.
+        The H2D copy, the kernel, the three D2H copies and one stream sync happen inside the call."""
+        if self._host is None:
+            B, L = self.num_envs, self.obs_dim
+            self._host = dict(
+                actions=torch.zeros(B, dtype=torch.float32).pin_memory(),
+                obs=torch.zeros(B, L, dtype=torch.float32).pin_memory(),
+                reward=torch.zeros(B, dtype=torch.float32).pin_memory(),
+                done=torch.zeros(B, dtype=torch.uint8).pin_memory())
+            self._host_np = {k: v.numpy() for k, v in self._host.items()}
+        h = self._host
+        np.copyto(self._host_np["actions"], np.asarray(actions, dtype=np.float32).reshape(-1))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_step_host(
+                self._p(), self._s(), h["actions"].data_ptr(), h["obs"].data_ptr(), h["reward"].data_ptr(),
+                h["done"].data_ptr(), self._actions_dev.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+                self.done_u8.data_ptr(), ctypes.byref(self._aux_full), self._stream()), "acas2d_step_host")
+        self.launches += 1
+        return self._host_np["obs"], self._host_np["reward"], self._host_np["done"].view(np.bool_)
+
+    # ------------------------------------------------------------------ synthetic rollouts
+    def random_actions(self, step_index: int, action_seed: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """U(-1,1) actions from the same Philox stream ``rollout_random`` draws in-kernel."""
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_random_actions(self._s(), action_seed, step_index, out.data_ptr(),
+                                                         self._stream()), "acas2d_random_actions")
+        self.launches += 1
+        return out
+
+    def rollout_random(self, num_steps: int, action_seed: int = 0, step0: int = 0,
+                       reward_sum: Optional[torch.Tensor] = None) -> None:
+        """``num_steps`` fused auto-resetting steps with in-kernel random actions (N_TRAFFIC == 1)."""
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_rollout_random(
+                self._p(), self._s(), int(num_steps), action_seed, step0,
+                reward_sum.data_ptr() if reward_sum is not None else None, self._stream()), "acas2d_rollout_random")
+        self.launches += 1
+
+    def capture_steps(self, actions: torch.Tensor, full_outputs: bool = False) -> "torch.cuda.CUDAGraph":
+        """Capture ``len(actions)`` consecutive steps (actions [K, B] resident in HBM) into one
+        CUDA graph; replay with ``graph.replay()``.  Launch-bound batches need this."""
+        actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        assert actions.dim() == 2 and actions.shape[1] == self.num_envs
+        self._graph_actions = actions
+        stream = torch.cuda.Stream(self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            self.step(actions[0], full_outputs)                      # warm-up outside capture
+            torch.cuda.current_stream(self.device).synchronize()
+            with torch.cuda.graph(graph, stream=stream):
+                for k in range(actions.shape[0]):
+                    self.step(actions[k], full_outputs)
+        torch.cuda.current_stream(self.device).wait_stream(stream)
+        return graph
+
+    # ------------------------------------------------------------------ state injection / extraction
+    def inject_state(self, player, traffic, steps=None, total_reward=None) -> None:
+        """Overwrite the games: ``player`` [B,3] = x, y, psi; ``traffic`` [B,N,4] = x, y, v_air, psi
+        (current position); ``steps`` [B] = game.steps (default 1, i.e. just reset);
+        ``total_reward`` [B].  Mirrors poking ``game.player`` / ``game.traffic`` in the reference."""
+        B, N, dev = self.num_envs, self.n_traffic, self.device
+        pl = torch.as_tensor(np.asarray(player, dtype=np.float64), device=dev).reshape(B, 3).contiguous()
+        tr = torch.as_tensor(np.asarray(traffic, dtype=np.float64), device=dev).reshape(B, N, 4).contiguous()
+        st = torch.ones(B, dtype=torch.int32, device=dev) if steps is None else \
+            torch.as_tensor(np.asarray(steps, dtype=np.int32), device=dev).reshape(B).contiguous()
+        tot = torch.zeros(B, dtype=torch.float64, device=dev) if total_reward is None else \
+            torch.as_tensor(np.asarray(total_reward, dtype=np.float64), device=dev).reshape(B).contiguous()
+        with torch.cuda.device(dev):
+            _native.check(self.lib.acas2d_inject_state(self._p(), self._s(), pl.data_ptr(), tr.data_ptr(),
+                                                       st.data_ptr(), tot.data_ptr(), self._stream()),
+                          "acas2d_inject_state")
+            torch.cuda.current_stream(dev).synchronize()            # staging tensors die with this frame
+        self.launches += 1
+
+    def extract_state(self) -> Dict[str, np.ndarray]:
+        """Current games as numpy float64: player [B,3], traffic [B,N,4], steps, total_reward, episode_idx."""
+        B, N, dev = self.num_envs, self.n_traffic, self.device
+        pl = torch.empty(B, 3, dtype=torch.float64, device=dev)
+        tr = torch.empty(B, N, 4, dtype=torch.float64, device=dev)
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        tot = torch.empty(B, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(self.lib.acas2d_extract_state(self._p(), self._s(), pl.data_ptr(), tr.data_ptr(),
+                                                        st.data_ptr(), tot.data_ptr(), self._stream()),
+                          "acas2d_extract_state")
+        self.launches += 1
+        out = dict(player=pl.cpu().numpy(), traffic=tr.cpu().numpy(), steps=st.cpu().numpy(),
+                   total_reward=tot.cpu().numpy(), episode_idx=self.episode_idx.cpu().numpy().astype(np.uint32))
+        if self.min_sep is not None:
+            out["min_sep"] = self.min_sep.cpu().numpy()
+        return out
+
+    _STATE_TENSORS = ("ppos", "paux", "tpos0", "tvel", "tpsi", "tvair", "episode_idx", "stats")
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Checkpoint of the env batch (the reference never saves env state)."""
+        d = {k: getattr(self, k).detach().clone() for k in self._STATE_TENSORS}
+        if self.min_sep is not None:
+            d["min_sep"] = self.min_sep.clone()
+        d["meta"] = torch.tensor([self.num_envs, self.n_traffic, self.seed, self.env_id_offset], dtype=torch.int64)
+        return d
+
+    def load_state_dict(self, d: Dict[str, torch.Tensor]) -> None:
+        meta = d["meta"].tolist()
+        if meta[0] != self.num_envs or meta[1] != self.n_traffic:
+            raise ValueError("state_dict was taken from a batch of a different shape")
+        for k in self._STATE_TENSORS:
+            getattr(self, k).copy_(d[k])
+        if self.min_sep is not None and "min_sep" in d:
+            self.min_sep.copy_(d["min_sep"])
+
+    # ------------------------------------------------------------------ episode statistics
+    def episode_counters(self) -> torch.Tensor:
+        """int64[7] device tensor: episodes, goal, collision, timeout, sum(length), sum(return)*2^20,
+        sum(min_sep)*2^20 -- finished episodes of THIS rank since construction / ``clear_stats``."""
+        return self.stats.sum(0)[: len(_native.STAT_NAMES)]
+
+    def clear_stats(self) -> None:
+        self.stats.zero_()
+
+    def episode_stats(self, reduce: bool = True) -> Dict[str, float]:
+        """Finished-episode statistics; summed over all ranks with one NCCL all-reduce of seven
+        int64 counters when ``torch.distributed`` is initialised and ``reduce`` is set."""
+        from .stats import summarise
+        return summarise(self.episode_counters(), reduce=reduce, track_min_sep=self.min_sep is not None)

@@ -1,0 +1,194 @@
+/*
+ * acas2d_b200.h -- C ABI of the B200-native batched ACAS-2D environment step.
+ *
+ * This library replaces ONE path of Christos-14/gym-ACAS2D: `ACAS2DEnv.reset/step`
+ * (reference gym_ACAS2D/envs/environment.py:29-48 and everything it calls in
+ * envs/game.py, envs/aircraft.py, envs/kinematics.py, envs/rewards.py).  The
+ * reference has no FFI layer -- its boundary is the Python gym.Env API -- so the
+ * entry points below are what a ctypes binding added to the reference's
+ * `environment.py` would call (see INTEGRATION.md for that stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every pointer in `acas2d_state` and every array argument is a DEVICE pointer
+ *     owned by the caller (PyTorch allocates them), except in `acas2d_step_host`.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocate, never synchronise (again except `acas2d_step_host`, which syncs the
+ *     stream once so the host buffers are valid on return).
+ *   - return value: 0 = ok, >0 = cudaError_t from the launch, <0 = ACAS2D_E_* below.
+ *   - one CUDA context per process/GPU; calls on different state objects are
+ *     independent and re-entrant.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Data layout in HBM (B = num_envs, N = n_traffic, L = 5 + 3N):
+ *   ppos        double[B][2]    player x, y                    (aircraft.py:9-10)
+ *   paux        16 B / env      { double psi; int32 steps; float ep_return }
+ *                               psi in degrees (aircraft.py:12); steps == game.steps
+ *                               (game.py:30,197); ep_return == game.total_reward so far
+ *                               (game.py:32,287)
+ *   tpos0       double[B][N][2] intruder position at steps == 1 (closed-form origin)
+ *   tvel        double[B][N][2] intruder displacement per step v*cos(psi)*dt, v*sin(psi)*dt;
+ *                               position after k moves = tpos0 + k * tvel (straight line,
+ *                               game.py:243-245; a_lat is always 0)
+ *   tpsi, tvair double[B][N]    intruder heading [deg] / speed: cold, touched by
+ *                               reset / inject / extract (tvair also by step when speeds differ, Q3)
+ *   episode_idx uint32[B]       episodes started by this env (Philox counter word 2)
+ *   min_sep     float[B]        running minimum separation of the episode, or NULL
+ *   stats       int64[ACAS2D_STAT_SLOTS][ACAS2D_STAT_FIELDS]  finished-episode counters
+ */
+#ifndef ACAS2D_B200_H
+#define ACAS2D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACAS2D_ABI_VERSION 1
+
+#define ACAS2D_E_NULL        (-1)  /* required pointer is NULL */
+#define ACAS2D_E_BAD_TRAFFIC (-2)  /* n_traffic < 1 (reference precondition, game.py:146-147) or > ACAS2D_MAX_TRAFFIC */
+#define ACAS2D_E_BAD_SIZE    (-3)  /* num_envs < 0 or exceeds int32 element indexing of an array */
+#define ACAS2D_E_NO_DEVICE   (-4)  /* no CUDA device / not an sm_100 device */
+
+#define ACAS2D_MAX_TRAFFIC 1024
+
+/* step flags (uint8 per env) */
+#define ACAS2D_FLAG_COLLISION 1u   /* game.py:185-189  d < 2*COLLISION_RADIUS for any intruder */
+#define ACAS2D_FLAG_GOAL      2u   /* game.py:191-192 */
+#define ACAS2D_FLAG_TIMEOUT   4u   /* game.py:182-183 */
+#define ACAS2D_FLAG_DONE      8u   /* game.py:294-310 */
+#define ACAS2D_FLAG_OOB       16u  /* aircraft.py:28-29, informational only: never ends an episode */
+
+/* outcome codes, settings.py:6 */
+#define ACAS2D_OUTCOME_GOAL 1
+#define ACAS2D_OUTCOME_COLLISION 2
+#define ACAS2D_OUTCOME_TIMEOUT 3
+
+/* finished-episode counters: stats[slot][field]; sum over slots on the host. */
+#define ACAS2D_STAT_SLOTS  128
+#define ACAS2D_STAT_FIELDS 16      /* 128 B per slot */
+#define ACAS2D_STAT_EPISODES   0
+#define ACAS2D_STAT_GOAL       1
+#define ACAS2D_STAT_COLLISION  2
+#define ACAS2D_STAT_TIMEOUT    3
+#define ACAS2D_STAT_LENGTH     4   /* sum of game.steps at episode end */
+#define ACAS2D_STAT_RETURN_FX  5   /* sum of total_reward, fixed point: value * 2^20 (order-independent) */
+#define ACAS2D_STAT_MINSEP_FX  6   /* sum of per-episode minimum separation * 2^20 (when tracked) */
+#define ACAS2D_STAT_FX_SCALE   1048576.0
+
+/* Constants of gym_ACAS2D/settings.py and the derived values of game.py:80-128. */
+typedef struct acas2d_params {
+    double width, height, fps;                 /* settings.py:15-17 */
+    double max_steps;                          /* settings.py:9 */
+    double aircraft_size;                      /* settings.py:33 */
+    double collision_radius;                   /* settings.py:34 */
+    double goal_radius;                        /* settings.py:35 */
+    double safe_distance;                      /* settings.py:36 */
+    double airspeed;                           /* settings.py:39 */
+    double airspeed_factor_min;                /* settings.py:40 */
+    double airspeed_factor_max;                /* settings.py:41 */
+    double acc_lat_limit;                      /* settings.py:42 */
+    double player_heading_lim;                 /* settings.py:43 */
+    double traffic_heading_lim;                /* settings.py:44 */
+    double reward_goal, reward_collision;      /* settings.py:47-48 */
+    double goal_x, goal_y;                     /* game.py:80-81 */
+    double player_x0, player_y0;               /* game.py:85-86 */
+    double player_psi_base;                    /* game.py:91 relative_angle(player -> goal), degrees */
+    double d_goal_max;                         /* game.py:120 */
+    double d_dev_max;                          /* game.py:122 */
+    double d_separation_max;                   /* game.py:124 */
+    double d_cpa_max;                          /* game.py:126 */
+    double v_closing_max;                      /* game.py:128 */
+    int32_t n_traffic;                         /* MIN_TRAFFIC == MAX_TRAFFIC, settings.py:31-32 */
+    int32_t auto_reset;                        /* 0: reference ACAS2DEnv semantics; 1: SB3 VecEnv auto-reset */
+} acas2d_params;
+
+typedef struct acas2d_state {
+    int64_t   num_envs;
+    void     *ppos;
+    void     *paux;
+    void     *tpos0;
+    void     *tvel;
+    double   *tpsi;
+    double   *tvair;
+    uint32_t *episode_idx;
+    float    *min_sep;        /* optional */
+    int64_t  *stats;          /* optional */
+    uint64_t  seed;           /* Philox key */
+    uint64_t  env_id_offset;  /* global id of env 0 (rank sharding: spawns do not depend on the GPU count) */
+} acas2d_state;
+
+/* Optional per-step outputs (any pointer may be NULL). */
+typedef struct acas2d_step_aux {
+    uint8_t *flags;      /* [B]     ACAS2D_FLAG_* of this step */
+    uint8_t *outcome;    /* [B]     written only where done */
+    float   *term_obs;   /* [B][L]  terminal observation, written only where done (auto_reset) */
+    float   *ep_return;  /* [B]     finished episode's total reward, written only where done */
+    int32_t *ep_length;  /* [B]     finished episode's game.steps, written only where done */
+} acas2d_step_aux;
+
+int acas2d_abi_version(void);
+
+/* settings.py defaults (+ derived values) for `n_traffic` intruders. */
+int acas2d_params_default(acas2d_params *params, int32_t n_traffic);
+
+/* Replaces ACAS2DEnv.reset() (environment.py:44-48 -> ACAS2DGame.__init__, game.py:27-160
+ * and game.observe, game.py:194-220) for every env whose mask byte is non-zero (all envs
+ * if mask == NULL).  Spawns come from Philox4x32-10 keyed by state->seed with counter
+ * (global env id, episode_idx, draw slot).  Writes the reset observation rows into obs
+ * (float[B][L], rows of unselected envs untouched; obs may be NULL). */
+int acas2d_reset(const acas2d_params *params, const acas2d_state *state,
+                 const uint8_t *mask, float *obs, void *stream);
+
+/* Replaces ACAS2DEnv.step() (environment.py:29-42: game.action -> observe -> evaluate ->
+ * is_done) for all B envs at once.  actions float[B] in [-1,1] (not clipped, game.py:225);
+ * obs float[B][L]; reward float[B]; done uint8[B].  With params->auto_reset the env is
+ * respawned on done and obs holds the reset observation (SB3 DummyVecEnv semantics). */
+int acas2d_step(const acas2d_params *params, const acas2d_state *state,
+                const float *actions, float *obs, float *reward, uint8_t *done,
+                const acas2d_step_aux *aux, void *stream);
+
+/* Same as acas2d_step but with HOST buffers for actions / obs / reward / done: copies
+ * actions host->device, steps, copies the three results device->host and synchronises
+ * `stream`.  d_* are caller-owned device staging buffers of the same shapes; h_* should be
+ * pinned for full PCIe rate. */
+int acas2d_step_host(const acas2d_params *params, const acas2d_state *state,
+                     const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done,
+                     float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
+                     const acas2d_step_aux *aux, void *stream);
+
+/* State injection / extraction (the reference's tests poke game.player / game.traffic
+ * attributes directly).  player double[B][3] = x, y, psi; traffic
+ * double[B][N][4] = x, y, v_air, psi (CURRENT position); steps int32[B] = game.steps;
+ * total_reward double[B].  Device pointers.  inject leaves episode_idx untouched and
+ * restarts min_sep from the injected geometry. */
+int acas2d_inject_state(const acas2d_params *params, const acas2d_state *state,
+                        const double *player, const double *traffic,
+                        const int32_t *steps, const double *total_reward, void *stream);
+int acas2d_extract_state(const acas2d_params *params, const acas2d_state *state,
+                         double *player, double *traffic,
+                         int32_t *steps, double *total_reward, void *stream);
+
+/* Synthetic benchmark path: K consecutive auto-resetting steps per launch with actions
+ * drawn in-kernel, a ~ U(-1,1) from Philox(key = action_seed, counter = (global env id,
+ * step0 + k)).  State stays in registers between the K steps; nothing but the state, the
+ * episode statistics and (optionally) reward_sum float[B] (+= sum of the K rewards) is
+ * written. */
+int acas2d_rollout_random(const acas2d_params *params, const acas2d_state *state,
+                          int32_t num_steps, uint64_t action_seed, uint64_t step0,
+                          float *reward_sum, void *stream);
+
+/* Fills actions float[B] with the same U(-1,1) stream acas2d_rollout_random uses for step
+ * `step_index` (so the per-step path can be checked against the fused path). */
+int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed,
+                          uint64_t step_index, float *actions, void *stream);
+
+/* Kernels launched by this library since load (all entry points). */
+int64_t acas2d_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACAS2D_B200_H */
