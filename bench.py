@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""ACAS-2D environment-step benchmark (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE pass of the hot path over one batch: ``step(actions[B])`` for all the envs a GPU
+owns.  Workload (``config.workload``): BASELINE.json config 3's random-action rollout at default
+N_TRAFFIC with auto-reset, at a per-GPU batch that saturates HBM (4 Mi envs / GPU -- SURVEY 8d:
+131 072 envs / GPU would be launch-bound), sharded by global env id, weak scaling.
+
+Prints ONE JSON line on rank 0.  ``value`` is env-steps/s with everything resident in HBM;
+``e2e`` is the same metric through the host-buffer C-ABI call (H2D actions, D2H obs / reward /
+done inside the timed region); ``roofline`` is algorithmic bytes / CUDA-event time against the
+measured HBM peak; ``cpu_baseline`` times the oracle port on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "gym-acas2d_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "env-steps/sec (whole box, device-timed)"
+UNIT = "env-steps/s"
+
+
+def shard(total: int, world: int, rank: int):
+    """Contiguous block of global env ids owned by ``rank``: (offset, count)."""
+    base, rem = divmod(total, world)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def algorithmic_bytes(n_traffic: int) -> int:
+    """A(N) = 69 + 32 N bytes per env-step (fp32 SoA, state read + written every step)."""
+    return 69 + 32 * n_traffic
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(n_traffic: int):
+    """DRAM bytes per env-step of the step kernel from the committed ncu capture, if any."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get(f"n{n_traffic}")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, device_index: int, period_s: float = 0.004):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.period = period_s
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baselines
+def _pyport_worker(args):
+    n_steps, seed = args
+    from oracle.acas2d_oracle import pyport_random_rollout
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        pyport_random_rollout(max(1, n_steps // 10), seed)          # warm-up
+        t0 = time.perf_counter()
+        pyport_random_rollout(n_steps, seed + 1)
+        return time.perf_counter() - t0
+
+
+def time_pyport(cores: int, steps_per_core: int):
+    """Reference-shaped scalar Python port (oracle/acas2d_oracle.py PyPortGame), one env per
+    process, random actions, resets included.  Returns env-steps/s summed over ``cores``."""
+    import multiprocessing as mp
+    if cores == 1:
+        dt = _pyport_worker((steps_per_core, 13))
+        return steps_per_core / dt
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_pyport_worker, [(steps_per_core, 13 + 17 * i) for i in range(cores)])
+    return cores * steps_per_core / max(times)
+
+
+def time_c_oracle(envs: int, steps: int):
+    """The C oracle (float64, one thread), auto-resetting random-action steps."""
+    import numpy as np
+    from oracle.acas2d_oracle import Oracle
+    orc = Oracle(1)
+    st = orc.new_state(envs)
+    orc.spawn_philox(st, 13, 0)
+    orc.observe(st)
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, (steps, envs))
+    orc.vec_step(st, acts[0], 13, 0)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        orc.vec_step(st, acts[k], 13, 0)
+    return envs * steps / (time.perf_counter() - t0)
+
+
+def cpu_baseline_block(budget_s: float = 12.0):
+    steps = 4000
+    rate1 = time_pyport(1, steps)
+    steps = int(min(max(rate1 * budget_s * 0.5, 2000), 200000))
+    rate1 = time_pyport(1, steps)
+    c_rate = time_c_oracle(8192, 64)
+    return {"value": rate1, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle Python port (reference-shaped scalar float64 code), 1 env, {steps} random-action "
+                      f"steps incl. resets, N_TRAFFIC=1; the reference itself is wall-clock capped at "
+                      f"100 steps/s (environment.py:31) and logged 69-89 steps/s (BASELINE.md)",
+            "c_oracle_1core": {"value": c_rate, "sample": "oracle C restatement, 8192 envs x 64 auto-reset steps, 1 thread"}}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on all host cores.
+    The reference is a Python program that cannot travel to the GPU box (no gym / pygame, and
+    /root/reference is absent there), so the oracle's Python port stands in (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 256                                   # env-steps per core per bench "step"
+    K, W = args.steps, args.warmup
+    K_eff = min(K, 400)                              # bounded: the whole run ends within minutes
+    t0 = time.perf_counter()
+    rate = time_pyport(cores, per_step * K_eff)
+    wall = time.perf_counter() - t0
+    sample = (f"{cores} processes x 1 env x {per_step * K_eff} random-action steps incl. resets "
+              f"(oracle Python port, N_TRAFFIC=1); steps capped at {K_eff} of the requested {K}")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * cores * per_step / rate,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "random-action rollout, default N_TRAFFIC=1, auto-reset, one env per host core",
+                       "envs": cores, "env_steps_per_step": cores * per_step},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gym_ACAS2D.envs import BatchedACAS2D, _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the ACAS-2D step has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = args.n_traffic
+    L = 5 + 3 * N
+    if args.total_envs:
+        offset, B = shard(args.total_envs, world, rank)
+        scaling = "strong"
+    else:
+        B = args.envs_per_gpu
+        offset = rank * B
+        scaling = "weak"
+    K, W = args.steps, args.warmup
+    lib = _native.load()
+
+    env = BatchedACAS2D(B, n_traffic=N, device=dev, seed=13, env_id_offset=offset, auto_reset=True)
+    env.reset()
+    KA = 8
+    actions = torch.empty(KA, B, dtype=torch.float32, device=dev)
+    for k in range(KA):
+        env.random_actions(k, action_seed=2024, out=actions[k])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        """CUDA-event time of ``iters`` calls of fn on the current stream, max over ranks (ms)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(iters):
+            fn(k)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput (the `value`)
+    step_fn = lambda k: env.step(actions[k % KA], full_outputs=False)   # noqa: E731
+    for k in range(W):
+        step_fn(k)
+    launches0 = lib.acas2d_launch_count()
+    with ClockSampler(local) as clocks:
+        ms = timed(step_fn, K)
+    launches = lib.acas2d_launch_count() - launches0
+    value = world * B * K / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    A = algorithmic_bytes(N)
+    achieved = A * B * K / (ms * 1e-3) / 1e9            # GB/s per GPU (max-over-ranks time)
+    stats = env.episode_stats(reduce=True)              # the one collective of the path (NCCL)
+
+    # ---- end to end through the host-buffer C-ABI call
+    import numpy as np
+    h_actions = actions[:KA].cpu().numpy()
+    Ke = max(3, min(args.e2e_steps, K))
+    for k in range(3):
+        env.step_host(h_actions[k % KA])
+    ms_e2e = timed(lambda k: env.step_host(h_actions[k % KA]), Ke)
+    e2e = world * B * Ke / (ms_e2e * 1e-3)
+
+    # ---- secondary workloads (reported, not the headline)
+    other = {}
+    if N == 1 and not args.skip_other:
+        env.rollout_random(8, action_seed=1, step0=0)
+        fused_k, reps = 64, 4
+        ms_f = timed(lambda k: env.rollout_random(fused_k, action_seed=1, step0=100 + fused_k * k), reps)
+        other["fused_rollout_64_steps_per_launch"] = {"value": world * B * fused_k * reps / (ms_f * 1e-3), "unit": UNIT,
+                                                      "note": "in-kernel Philox actions, state in registers, no per-step outputs"}
+        small = BatchedACAS2D(4096, n_traffic=1, device=dev, seed=13, env_id_offset=0, auto_reset=True)
+        small.reset()
+        graph = small.capture_steps(actions[:, :4096].contiguous().repeat(25, 1))      # 200 steps per replay
+        graph.replay()
+        ms_s = timed(lambda k: graph.replay(), 10)
+        other["config2_4096_envs_cuda_graph"] = {"value": world * 4096 * 200 * 10 / (ms_s * 1e-3), "unit": UNIT,
+                                                 "note": "BASELINE config 2 batch: launch-bound, 200-step CUDA graph replay"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "f64 flag chain + f32 observation/reward", "data": "synthetic",
+                "config": {"workload": "BASELINE config 3 random-action rollout at default N_TRAFFIC with auto-reset, "
+                                       "HBM-saturating batch per GPU (SURVEY 8d), sharded by global env id",
+                           "envs_per_gpu": B, "total_envs": world * B, "n_traffic": N, "obs_dim": L,
+                           "actions": f"pre-generated Philox U(-1,1) float32 [{KA},B] resident in HBM, cycled",
+                           "l2": "state + outputs per GPU = %.0f MB >> 126 MB L2 (no flush needed)" % (B * (A + 64) / 1e6),
+                           "parallelism": f"env-sharded x{world}, one all-reduce of 7 int64 episode counters after the timed region"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": ncu_traffic(N), "peak_source": peak_src,
+                             "algorithmic_bytes_per_env_step": A, "env_steps_per_launch": B,
+                             "note": "per GPU; achieved = A(N) x envs per launch / CUDA-event time per launch"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": (4 * L + 5) * B,
+                        "steps": Ke, "ms_per_step": ms_e2e / Ke,
+                        "path": "BatchedACAS2D.step_host -> acas2d_step_host (pinned host buffers)"},
+                "gpu_launches": int(launches), "clocks": clocks.summary(),
+                "episode_stats": stats, "other": other}
+        if world == 1 and not args.skip_cpu:
+            line["cpu_baseline"] = cpu_baseline_block()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--envs-per-gpu", type=int, default=4 * 1024 * 1024)
+    ap.add_argument("--total-envs", type=int, default=0, help="strong scaling: shard this many envs over the ranks")
+    ap.add_argument("--n-traffic", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-other", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,344 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (``BatchedACAS2D`` -> ctypes ->
+``libacas2d_b200.so``), against the float64 oracle and the reference fixtures.  Tolerances are
+stated in ``tests/parity.py``; flags, outcomes and episode lengths must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.acas2d_oracle import FLAG_DONE, Oracle
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import _native
+    _native.load()
+    return torch.device("cuda", 0)
+
+
+def make(B, n=1, **kw):
+    from gym_ACAS2D.envs import BatchedACAS2D
+    return BatchedACAS2D(B, n_traffic=n, device="cuda:0", **kw)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [1, 8])
+def test_reference_fixture_rollouts(cuda, golden_dir, n):
+    """Injected states x action sequences recorded from the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, f"ref_rollouts_n{n}.npz"))
+    B, T = g["player0"].shape[0], g["actions"].shape[0]
+    env = make(B, n, auto_reset=False)
+    parity.inject_from_fixture(env, g)
+    orc = Oracle(n)
+    st = orc.new_state(B)
+    st["player"][:] = g["player0"]; st["traffic"][:] = g["traffic0"]
+    st["steps"][:] = g["steps0"]; st["total_reward"][:] = g["total0"]
+    ref = orc.rollout(st, g["actions"].astype(np.float64))
+    rep = parity.ParityReport()
+    alive = np.ones(B, bool)
+    s = int(g["stride"])
+    acts = torch.from_numpy(g["actions"]).cuda()
+    for t in range(T):
+        obs, rew, _ = env.step(acts[t])
+        fobs, frew, fflags = parity.fixture_rows(g, t)
+        parity.compare_step(rep, npy(obs), npy(rew), npy(env.flags), fobs if fobs is not None else ref["obs"][t],
+                            frew, fflags, alive)
+        if t % (4 * s) == 0:
+            ex = env.extract_state()
+            assert np.abs(ex["player"][alive] - g["player_strided"][t // s][alive]).max(initial=0) < parity.TOL_POS
+            assert np.abs(ex["traffic"][alive][:, :, :2] - g["traffic_strided"][t // s][alive]).max(initial=0) < parity.TOL_POS
+        newly = alive & (fflags & FLAG_DONE > 0)
+        if newly.any():
+            assert np.array_equal(npy(env.outcome)[newly], g["outcome"][t][newly])
+            assert np.array_equal(npy(env.ep_length)[newly], g["steps"][newly])
+            assert np.abs(npy(env.ep_return)[newly] - g["total_reward"][newly]).max() < parity.TOL_RETURN
+        alive &= ~(fflags & FLAG_DONE > 0)
+    parity.assert_flags_exact(rep)
+    assert rep.steps > 3000
+
+
+def _random_states(rng, B, N):
+    """Random mid-air states + a share of threshold-grazing ones (collision / goal / timeout)."""
+    pl = np.c_[rng.uniform(30, 1300, B), rng.uniform(100, 900, B), rng.uniform(-40, 40, B) % 360]
+    tr = np.stack([rng.uniform(200, 1580, (B, N)), rng.uniform(20, 980, (B, N)),
+                   np.full((B, N), 200.0), rng.uniform(0, 360, (B, N))], -1)
+    steps = np.ones(B, np.int32)
+    k = B // 4
+    ang = rng.uniform(0, 2 * np.pi, k); d0 = rng.uniform(96.2, 130, k)          # closing head-on, just outside 96 px
+    tr[:k, 0, 0] = pl[:k, 0] + d0 * np.cos(ang); tr[:k, 0, 1] = pl[:k, 1] + d0 * np.sin(ang)
+    pl[:k, 2] = np.degrees(ang) % 360; tr[:k, 0, 3] = (np.degrees(ang) + 180) % 360
+    ang = rng.uniform(0, 2 * np.pi, k); d0 = rng.uniform(144.2, 200, k)         # flying into the goal disc
+    pl[k:2 * k, 0] = 1456 - d0 * np.cos(ang); pl[k:2 * k, 1] = 500 - d0 * np.sin(ang); pl[k:2 * k, 2] = np.degrees(ang) % 360
+    steps[2 * k:2 * k + k // 2] = rng.integers(900, 1001, k // 2)               # about to time out
+    return pl, tr, steps
+
+
+def test_config2_4096_envs_1001_steps_vs_oracle(cuda):
+    """BASELINE config 2: 4096 batched envs, default N_TRAFFIC, random actions, injected states,
+    1001 steps with auto-reset: every flag of ~4.1 M env-steps bit-exact, floats within tolerance."""
+    B, N, T, seed = 4096, 1, 1001, 13
+    rng = np.random.default_rng(42)
+    pl, tr, steps = _random_states(rng, B, N)
+    env = make(B, N, seed=seed, auto_reset=True, track_min_sep=True)
+    env.reset()
+    env.inject_state(pl, tr, steps)
+    orc = Oracle(N)
+    st = orc.new_state(B)
+    orc.spawn_philox(st, seed, 0)                      # episode 0 consumed, like env.reset()
+    st["player"][:, [0, 1, 3]] = pl; st["player"][:, 2] = 200.0; st["traffic"][:] = tr; st["steps"][:] = steps
+    d = tr[:, :, :2] - pl[:, None, :2]
+    st["min_sep"][:] = np.sqrt((d * d).sum(-1)).min(-1)
+    rep = parity.ParityReport()
+    acts = rng.uniform(-1, 1, (T, B)).astype(np.float32)
+    acts_d = torch.from_numpy(acts).cuda()
+    episodes = 0
+    for t in range(T):
+        obs, rew, done = env.step(acts_d[t])
+        o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, acts[t].astype(np.float64), seed, 0)
+        dn = f & FLAG_DONE > 0
+        assert np.array_equal(npy(done), dn)
+        obs_n = npy(obs)
+        cmp_obs = np.where(dn[:, None], npy(env.term_obs), obs_n)
+        parity.compare_step(rep, cmp_obs, npy(rew), npy(env.flags), np.where(dn[:, None], term, o), r, f)
+        if dn.any():
+            assert np.abs(obs_n[dn] - o[dn]).max() < parity.TOL_OBS_CPA
+            assert np.array_equal(npy(env.outcome)[dn], oc[dn])
+            assert np.array_equal(npy(env.ep_length)[dn], ep_len[dn])
+            assert np.abs(npy(env.ep_return)[dn] - ep_ret[dn]).max() < parity.TOL_RETURN
+            episodes += int(dn.sum())
+    parity.assert_flags_exact(rep)
+    assert rep.steps == B * T
+    ex = env.extract_state()
+    assert np.array_equal(ex["steps"], st["steps"])
+    assert np.array_equal(ex["episode_idx"], st["episode_idx"] + 1)
+    assert np.abs(ex["player"] - st["player"][:, [0, 1, 3]]).max() < parity.TOL_POS
+    assert np.abs(ex["traffic"][:, :, :2] - st["traffic"][:, :, :2]).max() < parity.TOL_POS
+    assert np.abs(ex["min_sep"] - st["min_sep"]).max() < 1e-3
+    c = npy(env.episode_counters())
+    assert c[0] == episodes and c[1] + c[2] + c[3] == episodes and episodes > B
+    print(rep)
+
+
+@pytest.mark.parametrize("n,B,T", [(2, 512, 300), (8, 512, 300), (64, 128, 120), (256, 64, 40)])
+def test_traffic_sweep_vs_oracle(cuda, n, B, T):
+    """BASELINE config 4 traffic counts (plus N=2): auto-reset rollouts vs the oracle."""
+    seed = 5
+    env = make(B, n, seed=seed, env_id_offset=77, auto_reset=True, track_min_sep=True)
+    orc = Oracle(n)
+    st = orc.new_state(B)
+    orc.spawn_philox(st, seed, 77)
+    ref0 = orc.observe(st)
+    assert np.nanmax(np.abs(npy(env.reset()) - ref0)) < parity.TOL_OBS_CPA
+    rng = np.random.default_rng(n)
+    rep = parity.ParityReport()
+    for t in range(T):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        obs, rew, done = env.step(torch.from_numpy(a).cuda())
+        o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, a.astype(np.float64), seed, 77)
+        dn = f & FLAG_DONE > 0
+        assert np.array_equal(npy(done), dn)
+        obs_n = npy(obs)
+        parity.compare_step(rep, np.where(dn[:, None], npy(env.term_obs), obs_n), npy(rew), npy(env.flags),
+                            np.where(dn[:, None], term, o), r, f)
+        if dn.any():
+            assert np.nanmax(np.abs(obs_n[dn] - o[dn])) < parity.TOL_OBS_CPA
+            assert np.array_equal(npy(env.ep_length)[dn], ep_len[dn])
+    assert rep.flag_mismatch == 0, rep
+    ex = env.extract_state()
+    assert np.array_equal(ex["episode_idx"], st["episode_idx"] + 1)
+    assert np.abs(ex["traffic"][:, :, :2] - st["traffic"][:, :, :2]).max() < parity.TOL_POS
+
+
+def test_sharding_invariance_and_determinism(cuda):
+    """1 Mi envs (BASELINE config 3 size): two half-batches addressed by global env id reproduce the
+    full batch bit for bit (state, outputs, integer episode counters) -- the multi-GPU property."""
+    B, T = 1 << 20, 24
+    full = make(B, 1, seed=9, auto_reset=True)
+    lo = make(B // 2, 1, seed=9, env_id_offset=0, auto_reset=True)
+    hi = make(B // 2, 1, seed=9, env_id_offset=B // 2, auto_reset=True)
+    o_full = full.reset().clone()
+    assert torch.equal(o_full[: B // 2], lo.reset()) and torch.equal(o_full[B // 2:], hi.reset())
+    # age the envs so that the short horizon crosses plenty of episode ends
+    for e in (full, lo, hi):
+        ex = e.extract_state()
+        ex["steps"][:] = 1 + (np.arange(e.env_id_offset, e.env_id_offset + e.num_envs) % 997)
+        e.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    for t in range(T):
+        a = full.random_actions(t, action_seed=4)
+        o, r, d = full.step(a)
+        o1, r1, d1 = lo.step(a[: B // 2])
+        o2, r2, d2 = hi.step(a[B // 2:])
+        assert torch.equal(o[: B // 2], o1) and torch.equal(o[B // 2:], o2)
+        assert torch.equal(r[: B // 2], r1) and torch.equal(d[B // 2:], d2)
+    assert torch.equal(full.episode_counters(), lo.episode_counters() + hi.episode_counters())
+    assert full.episode_counters()[0].item() > 10000
+    assert torch.equal(full.ppos[B // 2:], hi.ppos) and torch.equal(full.paux[: B // 2], lo.paux)
+    # action stream: global-id addressed too
+    assert torch.equal(full.random_actions(3, 8)[B // 2:], hi.random_actions(3, 8))
+
+
+def test_properties_at_full_size(cuda):
+    """Size-independent properties at 4 Mi envs (the bench batch): observation bounds of the declared
+    Box (apart from Q5's 1.001), reward range, done == any flag, timeout exactly at game.steps 1001,
+    straight flight covers AIRSPEED/FPS px per step."""
+    B = 4 << 20
+    env = make(B, 1, seed=1, auto_reset=True)
+    obs = env.reset()
+    assert obs.shape == (B, 8) and float(obs[:, 0].max()) == pytest.approx(0.001)
+    p0 = env.ppos.clone()
+    zero = torch.zeros(B, device="cuda")
+    for _ in range(5):
+        obs, rew, done = env.step(zero)
+    moved = (env.ppos - p0).norm(dim=1)
+    assert float((moved - 10.0).abs().max()) < 1e-9
+    lo = torch.tensor([0, 0, -1, 0, 0, 0, -1, -1], device="cuda", dtype=torch.float32)
+    for t in range(40):
+        obs, rew, done = env.step(env.random_actions(t, 3))
+        f = env.flags
+        assert torch.equal(done, (f & 7) != 0)
+        assert bool((obs >= lo).all()) and bool((obs <= 1.0011).all())
+        shaped = rew - 1000.0 * ((f & 2) != 0) + 1000.0 * ((f & 1) != 0)
+        assert float(shaped.min()) >= -2e-3 and float(shaped.max()) <= 1.0 + 1e-4
+    ex_steps = env.paux.view(torch.int32)[:, 2]
+    assert int(ex_steps.min()) >= 1 and int(ex_steps.max()) <= 1001
+
+
+def test_timeout_is_exactly_1000_step_calls(cuda):
+    """Q5/Q6: an episode is at most 1000 step() calls; final game.steps == 1001, obs[0] == 1.001, and the
+    time discount is -0.001 on that step."""
+    env = make(4, 1, auto_reset=False)
+    env.reset()
+    pl = np.tile([200.0, 500.0, 90.0], (4, 1)); pl[:, 1] = [100, 300, 500, 700]
+    tr = np.tile([1500.0, 50.0, 200.0, 0.0], (4, 1, 1))
+    env.inject_state(pl, tr, np.full(4, 998, np.int32))
+    a = torch.zeros(4, device="cuda")
+    o, r, d = env.step(a); assert not d.any() and float(o[0, 0]) == pytest.approx(0.999)
+    o, r, d = env.step(a); assert not d.any() and float(o[0, 0]) == pytest.approx(1.0)
+    o, r, d = env.step(a); assert d.all() and float(o[0, 0]) == pytest.approx(1.001)
+    assert (env.flags & 15 == 12).all() and (env.outcome == 3).all() and (env.ep_length == 1001).all()
+    assert float(r.max()) <= 0.0 and float(r.min()) > -0.0011
+
+
+def test_host_buffer_step_equals_device_step(cuda):
+    a = make(2048, 1, seed=2, auto_reset=True); b = make(2048, 1, seed=2, auto_reset=True)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    for t in range(50):
+        act = rng.uniform(-1, 1, 2048).astype(np.float32)
+        o1, r1, d1 = a.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = b.step_host(act)
+        assert np.array_equal(npy(o1), o2) and np.array_equal(npy(r1), r2) and np.array_equal(npy(d1), d2)
+
+
+def test_fused_rollout_equals_stepwise_and_graph(cuda):
+    B, K = 8192, 300
+    a = make(B, 1, seed=3, auto_reset=True); b = make(B, 1, seed=3, auto_reset=True); c = make(B, 1, seed=3, auto_reset=True)
+    for e in (a, b, c):
+        e.reset()
+    rs = torch.zeros(B, device="cuda")
+    a.rollout_random(K, action_seed=77, step0=0, reward_sum=rs)
+    acts = torch.stack([b.random_actions(k, 77) for k in range(K)])
+    acc = torch.zeros(B, device="cuda", dtype=torch.float64)
+    for k in range(K):
+        acc += b.step(acts[k])[1]
+    assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.tpos0, b.tpos0)
+    assert torch.equal(a.episode_counters(), b.episode_counters())
+    assert float((rs.double() - acc).abs().max()) < 0.5
+    # CUDA-graph replay of the step loop == eager (capture runs one warm-up step with actions[0])
+    c.step(acts[0])
+    graph = c.capture_steps(acts[1:])
+    # capture_steps' warm-up advanced c by acts[1]; rebuild c to the post-acts[0] state and replay
+    c2 = make(B, 1, seed=3, auto_reset=True); c2.reset(); c2.step(acts[0])
+    c.load_state_dict(c2.state_dict())
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(c.ppos, b.ppos) and torch.equal(c.paux, b.paux)
+
+
+def test_state_dict_roundtrip(cuda):
+    a = make(1000, 3, seed=8, auto_reset=True)
+    a.reset()
+    for t in range(30):
+        a.step(a.random_actions(t))
+    sd = a.state_dict()
+    b = make(1000, 3, seed=8, auto_reset=True)
+    b.load_state_dict(sd)
+    for t in range(30, 60):
+        act = a.random_actions(t)
+        oa = a.step(act)[0].clone()
+        assert torch.equal(oa, b.step(act)[0])
+
+
+def test_gym_surface_single_env(cuda):
+    """The reference's gym API (environment.py:8-54): spaces, reset -> float64[8], 4-tuple step,
+    env.game attributes; and an episode replayed through the oracle from the extracted state."""
+    import gym_ACAS2D
+    env = gym_ACAS2D.make("ACAS2D-v0")
+    assert env.observation_space.shape == (8,) and env.action_space.shape == (1,)
+    obs = env.reset()
+    assert obs.dtype == np.float64 and obs.shape == (8,) and env.observation_space.contains(obs)
+    assert obs[0] == pytest.approx(0.001) and env.game.steps == 1 and env.game.outcome is None
+    assert env.game.player.x == 48 and env.game.player.y == 500 and env.game.traffic[0].x == 1552
+    orc = Oracle(1)
+    st = orc.new_state(1)
+    ex = env._core.extract_state()
+    st["player"][0] = (ex["player"][0, 0], ex["player"][0, 1], 200.0, ex["player"][0, 2], 0.0)
+    st["traffic"][0] = ex["traffic"][0]; st["steps"][0] = 1
+    rng = np.random.default_rng(3)
+    for k in range(1100):
+        a = np.array([rng.uniform(-1, 1)], dtype=np.float32)
+        o, r, d, info = env.step(a)
+        ro, rr, rf, roc = orc.step(st, a.astype(np.float64))
+        assert isinstance(r, float) and isinstance(d, bool) and info == {} and o.dtype == np.float64
+        assert d == bool(rf[0] & FLAG_DONE)
+        assert np.abs(o - ro[0]).max() < 2e-6 and abs(r - rr[0]) < 2e-4
+        if d:
+            assert env.game.outcome == roc[0] and env.game.steps == st["steps"][0]
+            assert abs(env.game.total_reward - st["total_reward"][0]) < parity.TOL_RETURN
+            assert env.game.d_path == pytest.approx(st["d_path"][0], abs=1e-6)
+            break
+    assert d
+    # state injection through the game view (how the reference is poked)
+    env.reset()
+    env.game.player.x = 300.0; env.game.player.psi = 10.0; env.game.traffic[0].y = 640.0; env.game.steps = 17
+    assert env.game.player.x == 300.0 and env.game.player.psi == 10.0 and env.game.steps == 17
+    assert env.game.traffic[0].y == pytest.approx(640.0, abs=1e-9)
+    env.render(); env.close()
+
+
+def test_vec_env_adapter_semantics(cuda):
+    """SB3 DummyVecEnv semantics: terminal_observation + episode info on done, reset obs returned."""
+    from gym_ACAS2D.envs import ACAS2DVecEnv
+    B = 64
+    venv = ACAS2DVecEnv(B, seed=13)
+    assert venv.num_envs == B and venv.observation_space.shape == (8,) and venv.action_space.shape == (1,)
+    obs = venv.reset()
+    assert obs.shape == (B, 8) and obs.dtype == np.float32
+    orc = Oracle(1)
+    st = orc.new_state(B); orc.spawn_philox(st, 13, 0); orc.observe(st)
+    seen = 0
+    for t in range(800):
+        act = np.zeros((B, 1), np.float32)
+        obs, rew, dones, infos = venv.step(act)
+        o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, act[:, 0].astype(np.float64), 13, 0)
+        assert rew.dtype == np.float32 and dones.dtype == np.bool_ and len(infos) == B
+        assert np.array_equal(dones, f & FLAG_DONE > 0)
+        for i in np.flatnonzero(dones):
+            assert np.abs(infos[i]["terminal_observation"] - term[i]).max() < 2e-6
+            assert infos[i]["episode"]["l"] == ep_len[i] - 1 and abs(infos[i]["episode"]["r"] - ep_ret[i]) < parity.TOL_RETURN
+            assert abs(obs[i, 0] - 0.001) < 1e-7                                   # first obs of the next episode
+            seen += 1
+        assert all(infos[i] == {} for i in np.flatnonzero(~dones))
+    assert seen >= B
+    assert venv.env_is_wrapped(object) == [False] * B and venv.get_attr("num_envs")[0] == B
+    s = venv.core.episode_stats()
+    assert s["episodes"] == seen and s["timeout"] == 0
