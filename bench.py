@@ -228,6 +228,8 @@ def run_ours(args):
         scaling = "weak"
     K, W = args.steps, args.warmup
     lib = _native.load()
+    if args.n1_occ:
+        lib.acas2d_set_tuning(args.n1_occ, -1)
 
     env = BatchedACAS2D(B, n_traffic=N, device=dev, seed=13, env_id_offset=offset, auto_reset=True)
     env.reset()
@@ -333,6 +335,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true")
+    ap.add_argument("--n1-occ", type=int, default=0, help="experiment: 3|4 resident blocks/SM for the N=1 kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,13 +23,17 @@ typedef float4 Float4;
 struct alignas(16) Float4 { float x, y, z, w; };
 #endif
 
+// Cold full-precision complement of a traffic record (see acas2d_b200.h "tres").
+struct alignas(32) Residual { double x0, y0, psi, v; };
+
+constexpr int32_t kResidualBit = ACAS2D_STEPS_RESIDUAL_BIT;
+constexpr int32_t kStepsMask = ACAS2D_STEPS_RESIDUAL_BIT - 1;
+
 struct StatePtrs {
     Vec2d *ppos;
     PlayerAux *paux;
-    Vec2d *tpos0;
-    Vec2d *tvel;
-    double *tpsi;
-    double *tvair;
+    Float4 *thot;
+    Residual *tres;
     uint32_t *episode_idx;
     float *min_sep;
     long long *stats;
@@ -103,10 +107,8 @@ inline StatePtrs make_state_ptrs(const acas2d_state &s)
     StatePtrs o;
     o.ppos = (Vec2d *)s.ppos;
     o.paux = (PlayerAux *)s.paux;
-    o.tpos0 = (Vec2d *)s.tpos0;
-    o.tvel = (Vec2d *)s.tvel;
-    o.tpsi = s.tpsi;
-    o.tvair = s.tvair;
+    o.thot = (Float4 *)s.thot;
+    o.tres = (Residual *)s.tres;
     o.episode_idx = s.episode_idx;
     o.min_sep = s.min_sep;
     o.stats = (long long *)s.stats;
@@ -139,13 +141,71 @@ ACAS_HD void tally_add(Tally &t, int outcome, int steps, float ep_return, float 
     if (has_minsep) t.minsep_fx += llrint((double)minsep * ACAS2D_STAT_FX_SCALE);
 }
 
-// ---------------------------------------------------------------- N_TRAFFIC == 1
+// ---------------------------------------------------------------- traffic records
+// Hot record: float4 {x0, y0, psi, v}: position at game.steps == 1, heading [deg], speed.
+// Spawned intruders are float32-representable by construction (spawn_traffic rounds), so the
+// record is exact; injected float64 states keep their remainder in the cold Residual array and
+// set kResidualBit in PlayerAux.steps.  The intruder flies a straight line (game.py:243-245,
+// a_lat == 0): position after k moves = origin + k * (v cos psi dt, v sin psi dt), in float64.
+struct TrafficRec { double x0, y0, psi, v; };
+
+ACAS_HD TrafficRec traffic_load(const StatePtrs &S, int64_t ij, bool residual)
+{
+    const Float4 h = S.thot[ij];
+    TrafficRec t;
+    t.x0 = (double)h.x; t.y0 = (double)h.y; t.psi = (double)h.z; t.v = (double)h.w;
+    if (residual) {
+        const Residual r = S.tres[ij];
+        t.x0 += r.x0; t.y0 += r.y0; t.psi += r.psi; t.v += r.v;      // exact: r = full - float(full)
+    }
+    return t;
+}
+
+// Returns true when the record needed a residual (i.e. was not float32-representable).
+ACAS_HD bool traffic_store(const StatePtrs &S, int64_t ij, const TrafficRec &t, bool write_residual)
+{
+    Float4 h;
+    h.x = (float)t.x0; h.y = (float)t.y0; h.z = (float)t.psi; h.w = (float)t.v;
+    S.thot[ij] = h;
+    Residual r;
+    r.x0 = t.x0 - (double)h.x; r.y0 = t.y0 - (double)h.y; r.psi = t.psi - (double)h.z; r.v = t.v - (double)h.w;
+    const bool need = r.x0 != 0.0 || r.y0 != 0.0 || r.psi != 0.0 || r.v != 0.0;
+    if (write_residual) S.tres[ij] = r;
+    return need;
+}
+
+ACAS_HD Intruder intruder_at(const DevParams &P, const TrafficRec &t, int k)
+{
+    Intruder it;
+    heading_to_velocity(P, t.v, t.psi, &it.dx, &it.dy);
+    it.x = t.x0 + (double)k * it.dx;
+    it.y = t.y0 + (double)k * it.dy;
+    it.vratio = P.uniform_speed ? 1.0 : P.airspeed / t.v;              // Q3
+    return it;
+}
+
+// Spawn of intruder j of (gid, episode), rounded to float32 (game.py:97-114).
+ACAS_HD TrafficRec spawn_traffic(const DevParams &P, uint64_t seed, uint64_t gid, uint32_t episode, int j,
+                                 const Spawn0 &sp)
+{
+    TrafficRec t;
+    if (j == 0) { t.x0 = sp.x; t.y0 = sp.y; t.v = sp.v; t.psi = sp.psi; }
+    else {
+        const SpawnN sn = spawn_slot(P, seed, gid, episode, (uint32_t)j);
+        t.x0 = sn.x; t.y0 = sn.y; t.v = sn.v; t.psi = sn.psi;
+    }
+    t.x0 = (double)(float)t.x0; t.y0 = (double)(float)t.y0;
+    t.psi = (double)(float)t.psi; t.v = (double)(float)t.v;
+    return t;
+}
+
 // ---------------------------------------------------------------- N_TRAFFIC == 1
 struct Env1 {
     double px, py, psi;
-    int32_t steps;
+    int32_t steps;          // game.steps, without the residual bit
+    bool residual;
     float ret;
-    double t0x, t0y, tvx, tvy;
+    TrafficRec tr;
     float minsep;
     bool respawned;
 };
@@ -162,7 +222,7 @@ ACAS_HD void store_obs8(float *row, const PlayerView &v, const Encounter &e, con
 // EMIT = write per-step outputs through `out`; i = local env index.
 template <bool MINSEP, bool EMIT>
 ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float action,
-                                          int64_t i, const Sinks &out, Tally &tally, float *reward_acc)
+                       int64_t i, const Sinks &out, Tally &tally, float *reward_acc)
 {
     // ---- game.action (game.py:222-247)
     const double dpsi = (double)action * P.dpsi_per_action;               // game.py:225 + aircraft.py:20-22
@@ -171,17 +231,12 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
     player_set_heading(P, p, wrap360(e.psi + dpsi), dpsi);
     player_advance(P, p);
 
-    Intruder t;
-    t.dx = e.tvx; t.dy = e.tvy;
-    t.vratio = 1.0;
-    if (!P.uniform_speed) t.vratio = P.airspeed / S.tvair[i];              // Q3
     const int k = e.steps;                                                 // intruder moves after this step
+    Intruder t = intruder_at(P, e.tr, k);                                  // game.py:243-245
     if (MINSEP) {                                                          // game.py:237 (Q10: old traffic)
-        const double ox = (e.t0x + (double)(k - 1) * t.dx) - p.x, oy = (e.t0y + (double)(k - 1) * t.dy) - p.y;
+        const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
         e.minsep = fminf(e.minsep, sqrtf((float)(ox * ox + oy * oy)));
     }
-    t.x = e.t0x + (double)k * t.dx;                                        // game.py:243-245
-    t.y = e.t0y + (double)k * t.dy;
 
     // ---- game.observe / evaluate / is_done (game.py:194-314)
     const int steps = k + 1;                                               // game.py:197
@@ -236,19 +291,17 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
 
     const uint32_t episode = S.episode_idx[i];
     S.episode_idx[i] = episode + 1u;
-    const Spawn0 sp = spawn_slot0(P, S.seed, S.gid0 + (uint64_t)i, episode);
+    const uint64_t gid = S.gid0 + (uint64_t)i;
+    const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
     p.x = P.player_x0; p.y = P.player_y0;
     player_set_heading(P, p, sp.player_psi, 0.0);                          // a_lat = 0 in a new game
-    heading_to_velocity(P, sp.v, sp.psi, &t.dx, &t.dy);
-    t.x = sp.x; t.y = sp.y;
-    t.vratio = P.airspeed / sp.v;
-    S.tpsi[i] = sp.psi;
-    S.tvair[i] = sp.v;
+    e.tr = spawn_traffic(P, S.seed, gid, episode, 0, sp);
+    t = intruder_at(P, e.tr, 0);
     const PlayerView v1 = player_view(P, p, 1);                            // environment.py:47: steps becomes 1
     const Encounter e1 = encounter(P, p, t);
     if (EMIT) store_obs8(out.obs + 8 * i, v1, e1, P);
     e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = 1; e.ret = 0.0f;
-    e.t0x = t.x; e.t0y = t.y; e.tvx = t.dx; e.tvy = t.dy;
+    e.residual = false;
     e.minsep = e1.d;                                                       // game.py:141
     e.respawned = true;
 }
@@ -257,10 +310,10 @@ ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
 {
     const Vec2d pp = S.ppos[i];
     const PlayerAux pa = S.paux[i];
-    const Vec2d t0 = S.tpos0[i];
-    const Vec2d tv = S.tvel[i];
-    e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.steps = pa.steps; e.ret = pa.ep_return;
-    e.t0x = t0.x; e.t0y = t0.y; e.tvx = tv.x; e.tvy = tv.y;
+    e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.ret = pa.ep_return;
+    e.steps = pa.steps & kStepsMask;
+    e.residual = (pa.steps & kResidualBit) != 0;
+    e.tr = traffic_load(S, i, e.residual);
     e.minsep = minsep ? S.min_sep[i] : 0.0f;
     e.respawned = false;
 }
@@ -268,22 +321,16 @@ ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
 ACAS_HD void store_env1(const StatePtrs &S, int64_t i, const Env1 &e, bool minsep)
 {
     Vec2d pp; pp.x = e.px; pp.y = e.py;
-    PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps; pa.ep_return = e.ret;
+    PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps | (e.residual ? kResidualBit : 0); pa.ep_return = e.ret;
     S.ppos[i] = pp;
     S.paux[i] = pa;
-    if (e.respawned) {
-        Vec2d t0; t0.x = e.t0x; t0.y = e.t0y;
-        Vec2d tv; tv.x = e.tvx; tv.y = e.tvy;
-        S.tpos0[i] = t0;
-        S.tvel[i] = tv;
-    }
+    if (e.respawned) traffic_store(S, i, e.tr, false);
     if (minsep) S.min_sep[i] = e.minsep;
 }
 
-
 // ---------------------------------------------------------------- any N_TRAFFIC, one thread per env
 // Intruders streamed straight from global memory.  Correct for every N; it is the simple
-// form the shared-memory tiled kernel is checked against and the fallback for exotic N.
+// form the shared-memory tiled kernel is checked against.
 template <bool MINSEP>
 ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, float action,
                            const Sinks &out, Tally &tally)
@@ -292,31 +339,25 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
     const int L = 5 + 3 * N;
     const Vec2d pp = S.ppos[i];
     const PlayerAux pa = S.paux[i];
+    const bool residual = (pa.steps & kResidualBit) != 0;
     const double dpsi = (double)action * P.dpsi_per_action;
     Player p;
     p.x = pp.x; p.y = pp.y;
     player_set_heading(P, p, wrap360(pa.psi + dpsi), dpsi);
     player_advance(P, p);
-    const int k = pa.steps;
+    const int k = pa.steps & kStepsMask;
     const int steps = k + 1;
     const PlayerView v = player_view(P, p, steps);
     float *row = out.obs + (int64_t)L * i;
-    float *trow = nullptr;
     bool coll = false;
     float minsep = MINSEP ? S.min_sep[i] : 0.0f;
     Encounter e0;
     for (int j = 0; j < N; ++j) {
-        const int64_t ij = i * N + j;
-        const Vec2d t0 = S.tpos0[ij], tv = S.tvel[ij];
-        Intruder t;
-        t.dx = tv.x; t.dy = tv.y;
-        t.vratio = P.uniform_speed ? 1.0 : P.airspeed / S.tvair[ij];
+        const Intruder t = intruder_at(P, traffic_load(S, i * N + j, residual), k);
         if (MINSEP) {
-            const double ox = (t0.x + (double)(k - 1) * t.dx) - p.x, oy = (t0.y + (double)(k - 1) * t.dy) - p.y;
+            const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
             minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
         }
-        t.x = t0.x + (double)k * t.dx;
-        t.y = t0.y + (double)k * t.dy;
         const Encounter en = encounter(P, p, t);
         if (j == 0) e0 = en;
         coll |= en.d2 < P.coll_d2;
@@ -343,7 +384,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
                                  (tout ? ACAS2D_FLAG_TIMEOUT : 0) | (done ? ACAS2D_FLAG_DONE : 0) |
                                  (oob ? ACAS2D_FLAG_OOB : 0));
     }
-    int steps_out = steps;
+    int steps_out = steps | (residual ? kResidualBit : 0);
     if (done) {
         if (out.outcome) out.outcome[i] = (uint8_t)outcome;
         if (out.ep_return) out.ep_return[i] = ret;
@@ -351,7 +392,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
         tally_add(tally, outcome, steps, ret, minsep, MINSEP);
         if (P.auto_reset) {
             if (out.term_obs) {
-                trow = out.term_obs + (int64_t)L * i;
+                float *trow = out.term_obs + (int64_t)L * i;
                 for (int q = 0; q < L; ++q) trow[q] = row[q];
             }
             const uint32_t episode = S.episode_idx[i];
@@ -365,18 +406,9 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             for (int q = 0; q < 5; ++q) row[q] = v1.obs[q];
             minsep = INFINITY;
             for (int j = 0; j < N; ++j) {
-                const int64_t ij = i * N + j;
-                SpawnN sn;
-                if (j == 0) { sn.x = sp.x; sn.y = sp.y; sn.v = sp.v; sn.psi = sp.psi; }
-                else sn = spawn_slot(P, S.seed, gid, episode, (uint32_t)j);
-                Intruder t;
-                heading_to_velocity(P, sn.v, sn.psi, &t.dx, &t.dy);
-                t.x = sn.x; t.y = sn.y;
-                t.vratio = P.airspeed / sn.v;
-                Vec2d a; a.x = t.x; a.y = t.y;
-                Vec2d b; b.x = t.dx; b.y = t.dy;
-                S.tpos0[ij] = a; S.tvel[ij] = b; S.tpsi[ij] = sn.psi; S.tvair[ij] = sn.v;
-                const Encounter en = encounter(P, p, t);
+                const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
+                traffic_store(S, i * N + j, tr, false);
+                const Encounter en = encounter(P, p, intruder_at(P, tr, 0));
                 minsep = fminf(minsep, en.d);
                 row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
                 row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
@@ -411,18 +443,9 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     if (row) for (int q = 0; q < 5; ++q) row[q] = v.obs[q];
     float minsep = INFINITY;
     for (int j = 0; j < N; ++j) {
-        const int64_t ij = i * N + j;
-        SpawnN sn;
-        if (j == 0) { sn.x = sp.x; sn.y = sp.y; sn.v = sp.v; sn.psi = sp.psi; }
-        else sn = spawn_slot(P, S.seed, gid, episode, (uint32_t)j);
-        Intruder t;
-        heading_to_velocity(P, sn.v, sn.psi, &t.dx, &t.dy);
-        t.x = sn.x; t.y = sn.y;
-        t.vratio = P.airspeed / sn.v;
-        Vec2d a; a.x = t.x; a.y = t.y;
-        Vec2d b; b.x = t.dx; b.y = t.dy;
-        S.tpos0[ij] = a; S.tvel[ij] = b; S.tpsi[ij] = sn.psi; S.tvair[ij] = sn.v;
-        const Encounter en = encounter(P, p, t);
+        const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
+        traffic_store(S, i * N + j, tr, false);
+        const Encounter en = encounter(P, p, intruder_at(P, tr, 0));
         minsep = fminf(minsep, en.d);
         if (row) {
             row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
@@ -442,21 +465,26 @@ ACAS_HD void inject_env(const DevParams &P, const StatePtrs &S, int64_t i, const
 {
     const int N = P.n_traffic;
     Vec2d np; np.x = player[3 * i]; np.y = player[3 * i + 1];
-    PlayerAux na; na.psi = player[3 * i + 2]; na.steps = steps[i]; na.ep_return = (float)total_reward[i];
-    S.ppos[i] = np;
-    S.paux[i] = na;
+    const int st = steps[i] & kStepsMask;
     float minsep = INFINITY;
-    const double back = (double)(na.steps - 1);
+    const double back = (double)(st - 1);
+    bool residual = false;
     for (int j = 0; j < N; ++j) {
         const int64_t ij = i * N + j;
-        const double x = traffic[4 * ij], y = traffic[4 * ij + 1], v = traffic[4 * ij + 2], psi = traffic[4 * ij + 3];
-        Vec2d b;
-        heading_to_velocity(P, v, psi, &b.x, &b.y);
-        Vec2d a; a.x = x - back * b.x; a.y = y - back * b.y;       // closed-form origin (steps == 1)
-        S.tpos0[ij] = a; S.tvel[ij] = b; S.tpsi[ij] = psi; S.tvair[ij] = v;
+        TrafficRec tr;
+        const double x = traffic[4 * ij], y = traffic[4 * ij + 1];
+        tr.v = traffic[4 * ij + 2]; tr.psi = traffic[4 * ij + 3];
+        double dx, dy;
+        heading_to_velocity(P, tr.v, tr.psi, &dx, &dy);
+        tr.x0 = x - back * dx; tr.y0 = y - back * dy;               // closed-form origin (steps == 1)
+        residual |= traffic_store(S, ij, tr, true);
         const double ox = x - np.x, oy = y - np.y;
         minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
     }
+    PlayerAux na; na.psi = player[3 * i + 2]; na.ep_return = (float)total_reward[i];
+    na.steps = st | (residual ? kResidualBit : 0);
+    S.ppos[i] = np;
+    S.paux[i] = na;
     if (S.min_sep) S.min_sep[i] = minsep;
 }
 
@@ -466,18 +494,19 @@ ACAS_HD void extract_env(const DevParams &P, const StatePtrs &S, int64_t i, doub
     const int N = P.n_traffic;
     const Vec2d pp = S.ppos[i];
     const PlayerAux pa = S.paux[i];
+    const int st = pa.steps & kStepsMask;
     if (player) { player[3 * i] = pp.x; player[3 * i + 1] = pp.y; player[3 * i + 2] = pa.psi; }
-    if (steps) steps[i] = pa.steps;
+    if (steps) steps[i] = st;
     if (total_reward) total_reward[i] = (double)pa.ep_return;
     if (traffic) {
-        const double k = (double)(pa.steps - 1);
         for (int j = 0; j < N; ++j) {
             const int64_t ij = i * N + j;
-            const Vec2d a = S.tpos0[ij], b = S.tvel[ij];
-            traffic[4 * ij + 0] = a.x + k * b.x;
-            traffic[4 * ij + 1] = a.y + k * b.y;
-            traffic[4 * ij + 2] = S.tvair[ij];
-            traffic[4 * ij + 3] = S.tpsi[ij];
+            const TrafficRec tr = traffic_load(S, ij, (pa.steps & kResidualBit) != 0);
+            const Intruder t = intruder_at(P, tr, st - 1);
+            traffic[4 * ij + 0] = t.x;
+            traffic[4 * ij + 1] = t.y;
+            traffic[4 * ij + 2] = tr.v;
+            traffic[4 * ij + 3] = tr.psi;
         }
     }
 }

@@ -19,6 +19,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/acas2d_b200.h"
@@ -38,7 +39,7 @@ int check_args(const acas2d_params *p, const acas2d_state *s)
     if (!p || !s) return ACAS2D_E_NULL;
     if (p->n_traffic < 1 || p->n_traffic > ACAS2D_MAX_TRAFFIC) return ACAS2D_E_BAD_TRAFFIC;
     if (s->num_envs < 0 || s->num_envs * (int64_t)(5 + 3 * p->n_traffic) > (int64_t)1 << 40) return ACAS2D_E_BAD_SIZE;
-    if (!s->ppos || !s->paux || !s->tpos0 || !s->tvel || !s->tpsi || !s->tvair || !s->episode_idx)
+    if (!s->ppos || !s->paux || !s->thot || !s->tres || !s->episode_idx)
         return ACAS2D_E_NULL;
     return 0;
 }
@@ -47,6 +48,22 @@ int finish_launch()
 {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
+}
+
+// Tuning knobs for experiments (read once): ACAS2D_N1_OCC = 3|4 blocks/SM for the N == 1 kernel,
+// ACAS2D_FORCE_LOOP = 1 routes N > 1 to the simple per-thread kernel the tiled one is checked against.
+struct Tuning { int n1_occupancy; bool force_loop; };
+Tuning &tuning()
+{
+    static Tuning t = [] {
+        Tuning x;
+        const char *o = std::getenv("ACAS2D_N1_OCC");
+        x.n1_occupancy = (o && std::atoi(o) == 3) ? 3 : 4;
+        const char *f = std::getenv("ACAS2D_FORCE_LOOP");
+        x.force_loop = f && std::atoi(f) != 0;
+        return x;
+    }();
+    return t;
 }
 
 // ---------------------------------------------------------------- warp-level statistics flush
@@ -84,8 +101,8 @@ __device__ __forceinline__ void tally_flush_warp(long long *stats, const Tally &
     }
 }
 
-template <bool MINSEP>
-__global__ void __launch_bounds__(kBlock)
+template <bool MINSEP, int OCC>
+__global__ void __launch_bounds__(kBlock, OCC)
 step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -134,6 +151,241 @@ step_loop_kernel(const DevParams P, const StatePtrs S, const float *__restrict__
     tally_clear(tally);
     if (i < S.B) step_env_loop<MINSEP>(P, S, i, actions[i], out, tally);
     tally_flush_warp(S.stats, tally);
+}
+
+// ---------------------------------------------------------------- N_TRAFFIC > 1: shared-memory tiled
+// G lanes cooperate on one env (G = 1, 2, ..., 32; G divides N), so a warp owns E = 32/G
+// consecutive envs and every lane handles N/G intruders (about eight: the instruction budget of an
+// HBM-bound step does not allow a whole warp per env below N = 256).
+//   1. the warp's traffic tile -- E*N float4 records, contiguous in HBM -- is staged into shared
+//      memory with coalesced 16-byte cp.async copies while the player update runs;
+//   2. each lane walks its intruders (rotated start, so the 16-byte shared loads of a quarter warp
+//      fall in distinct banks), keeps collision / min-separation partials in registers and writes
+//      the three observation entries of each intruder into the warp's observation tile;
+//   3. any-collision and min-separation are reduced over the G lanes with xor shuffles;
+//   4. lane 0 of each group finishes reward / flags / episode bookkeeping;
+//   5. finished envs respawn cooperatively (one Philox block per intruder) and re-observe;
+//   6. the observation tile is written back row by row, fully coalesced.
+constexpr int kTiledWarps = 4;
+
+__host__ __device__ inline int tiled_obs_stride(int L, int G) { return (G == 1 && (L & 1)) ? L + 1 : L; }
+
+inline size_t tiled_smem_bytes(int N, int G)
+{
+    const int E = 32 / G, L = 5 + 3 * N;
+    return (size_t)kTiledWarps * ((size_t)E * N * 16 + (((size_t)E * tiled_obs_stride(L, G) * 4 + 15) & ~(size_t)15));
+}
+
+template <int G, bool MINSEP>
+__global__ void __launch_bounds__(kTiledWarps * 32)
+step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out)
+{
+    constexpr int E = 32 / G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P.n_traffic;
+    const int L = 5 + 3 * N;
+    const int Lp = tiled_obs_stride(L, G);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t warp_bytes = (size_t)E * N * 16 + (((size_t)E * Lp * 4 + 15) & ~(size_t)15);
+    Float4 *tile = (Float4 *)(smem_raw + warp * warp_bytes);
+    float *otile = (float *)(smem_raw + warp * warp_bytes + (size_t)E * N * 16);
+
+    const int64_t env0 = ((int64_t)blockIdx.x * kTiledWarps + warp) * E;     // first env of this warp
+    Tally tally;
+    tally_clear(tally);
+    if (env0 < S.B) {                                                       // warp-uniform
+        const int nvalid = (int)((S.B - env0) < (int64_t)E ? (S.B - env0) : (int64_t)E);
+        const int e = lane / G, sub = lane % G;
+        const bool valid = e < nvalid;
+        const int64_t env = env0 + (valid ? e : 0);
+        const bool lead = valid && sub == 0;
+
+        // 1. stage the traffic tile
+        {
+            const Float4 *src = S.thot + env0 * N;
+            const int total = nvalid * N;
+            for (int idx = lane; idx < total; idx += 32)
+                __pipeline_memcpy_async(tile + idx, src + idx, 16);
+            __pipeline_commit();
+        }
+
+        // player update, redundantly in every lane of the group (game.py:222-229)
+        const Vec2d pp = S.ppos[env];
+        const PlayerAux pa = S.paux[env];
+        const bool residual = (pa.steps & kResidualBit) != 0;
+        const double dpsi = (double)actions[env] * P.dpsi_per_action;
+        Player p;
+        p.x = pp.x; p.y = pp.y;
+        player_set_heading(P, p, wrap360(pa.psi + dpsi), dpsi);
+        player_advance(P, p);
+        const int k = pa.steps & kStepsMask;
+        const int steps = k + 1;
+        float minsep = (MINSEP && lead) ? S.min_sep[env] : INFINITY;
+
+        __pipeline_wait_prior(0);
+        __syncwarp();
+
+        // 2. intruders of this lane
+        const int per_lane = N / G;
+        int j = lane % N;                              // rotated start; j == sub (mod G) because G | N
+        bool coll = false;
+        Encounter e0;
+        e0.d2 = 0.0; e0.d = 0.0f; e0.d_cpa = 0.0f; e0.v_c = 0.0f;
+        float *orow = otile + e * Lp;
+        for (int m = 0; m < per_lane; ++m) {
+            const Float4 h = tile[e * N + j];
+            TrafficRec tr;
+            tr.x0 = (double)h.x; tr.y0 = (double)h.y; tr.psi = (double)h.z; tr.v = (double)h.w;
+            if (residual) {
+                const Residual r = S.tres[env * N + j];
+                tr.x0 += r.x0; tr.y0 += r.y0; tr.psi += r.psi; tr.v += r.v;
+            }
+            const Intruder t = intruder_at(P, tr, k);
+            if (MINSEP) {
+                const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
+                minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
+            }
+            const Encounter en = encounter(P, p, t);
+            if (j == 0) e0 = en;
+            coll |= en.d2 < P.coll_d2;
+            orow[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
+            orow[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
+            orow[5 + 3 * j + 2] = en.v_c * P.vc_scale;
+            j += G;
+            if (j >= N) j -= N;
+        }
+
+        // 3. reductions over the G lanes of the env
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            coll |= (bool)__shfl_xor_sync(kFull, (int)coll, o);
+            if (MINSEP) minsep = fminf(minsep, __shfl_xor_sync(kFull, minsep, o));
+        }
+
+        // 4. player-side observation, reward, flags (lane `sub == 0` owns intruder 0, Q7)
+        const PlayerView v = player_view(P, p, steps);
+        float r = shaped_reward(P, p, v, e0, steps);
+        const bool goal = v.dg2 < P.goal_r2;
+        const bool tout = steps > P.max_steps;
+        if (coll) r += P.reward_collision;
+        if (goal) r += P.reward_goal;
+        float ret = pa.ep_return + r;
+        const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
+                            : goal ? ACAS2D_OUTCOME_GOAL : 0;
+        const bool done = outcome != 0;
+        int steps_out = steps | (residual ? kResidualBit : 0);
+        if (lead) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) orow[q] = v.obs[q];
+            out.reward[env] = r;
+            out.done[env] = (uint8_t)done;
+            if (out.flags) {
+                const bool oob = p.x < 0.0 || p.x > P.width || p.y < 0.0 || p.y > P.height;
+                out.flags[env] = (uint8_t)((coll ? ACAS2D_FLAG_COLLISION : 0) | (goal ? ACAS2D_FLAG_GOAL : 0) |
+                                           (tout ? ACAS2D_FLAG_TIMEOUT : 0) | (done ? ACAS2D_FLAG_DONE : 0) |
+                                           (oob ? ACAS2D_FLAG_OOB : 0));
+            }
+            if (done) {
+                if (out.outcome) out.outcome[env] = (uint8_t)outcome;
+                if (out.ep_return) out.ep_return[env] = ret;
+                if (out.ep_length) out.ep_length[env] = steps;
+                tally_add(tally, outcome, steps, ret, minsep, MINSEP);
+            }
+        }
+
+        // 5. auto-reset of the finished envs of this warp
+        const bool respawn = valid && done && P.auto_reset;
+        const unsigned respawn_mask = __ballot_sync(kFull, respawn);
+        if (respawn_mask) {
+            __syncwarp();
+            if (out.term_obs) {
+                for (int row = 0; row < nvalid; ++row) {
+                    if (!((respawn_mask >> (row * G)) & 1u)) continue;          // warp-uniform
+                    float *dst = out.term_obs + (env0 + row) * L;
+                    for (int c = lane; c < L; c += 32) dst[c] = otile[row * Lp + c];
+                }
+                __syncwarp();
+            }
+            if (respawn) {
+                uint32_t episode = 0;
+                if (sub == 0) { episode = S.episode_idx[env]; S.episode_idx[env] = episode + 1u; }
+                episode = __shfl_sync(__activemask(), episode, e * G);
+                const uint64_t gid = S.gid0 + (uint64_t)env;
+                const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
+                p.x = P.player_x0; p.y = P.player_y0;
+                player_set_heading(P, p, sp.player_psi, 0.0);
+                minsep = INFINITY;
+                j = lane % N;
+                for (int m = 0; m < per_lane; ++m) {
+                    const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
+                    traffic_store(S, env * N + j, tr, false);
+                    const Encounter en = encounter(P, p, intruder_at(P, tr, 0));
+                    minsep = fminf(minsep, en.d);
+                    orow[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
+                    orow[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
+                    orow[5 + 3 * j + 2] = en.v_c * P.vc_scale;
+                    j += G;
+                    if (j >= N) j -= N;
+                }
+                if (sub == 0) {
+                    const PlayerView v1 = player_view(P, p, 1);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) orow[q] = v1.obs[q];
+                }
+                steps_out = 1;
+                ret = 0.0f;
+            }
+            if (MINSEP) {      // min over the group of the spawn separations (game.py:141)
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) minsep = fminf(minsep, __shfl_xor_sync(kFull, minsep, o));
+            }
+        }
+        __syncwarp();
+
+        // 6. coalesced write-back of the observation rows
+        for (int row = 0; row < nvalid; ++row) {
+            float *dst = out.obs + (env0 + row) * L;
+            for (int c = lane; c < L; c += 32) __stcs(dst + c, otile[row * Lp + c]);
+        }
+
+        if (lead) {
+            Vec2d np; np.x = p.x; np.y = p.y;
+            PlayerAux na; na.psi = p.psi; na.steps = steps_out; na.ep_return = ret;
+            S.ppos[env] = np;
+            S.paux[env] = na;
+            if (MINSEP) S.min_sep[env] = minsep;
+        }
+    }
+    tally_flush_warp(S.stats, tally);
+}
+
+inline int tiled_group(int N)
+{
+    int want = 1;
+    while (want < 32 && want * 8 < N) want <<= 1;        // about eight intruders per lane
+    int g = 1;
+    while (g < want && N % (g * 2) == 0) g <<= 1;         // G must divide N
+    return g;
+}
+
+template <int G>
+int launch_tiled(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
+{
+    constexpr int E = 32 / G;
+    const size_t smem = tiled_smem_bytes(P.n_traffic, G);
+    const int64_t warps = (S.B + E - 1) / E;
+    const unsigned grid = (unsigned)((warps + kTiledWarps - 1) / kTiledWarps);
+    cudaError_t err;
+    if (S.min_sep) {
+        err = cudaFuncSetAttribute(step_tiled_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        step_tiled_kernel<G, true><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out);
+    } else {
+        err = cudaFuncSetAttribute(step_tiled_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        step_tiled_kernel<G, false><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out);
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------- reset / inject / extract
@@ -244,11 +496,28 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
     const unsigned grid = grid_for(state->num_envs);
     cudaStream_t st = (cudaStream_t)stream;
     if (P.n_traffic == 1) {
-        if (S.min_sep) step_n1_kernel<true><<<grid, kBlock, 0, st>>>(P, S, actions, out);
-        else step_n1_kernel<false><<<grid, kBlock, 0, st>>>(P, S, actions, out);
-    } else {
+        const bool occ4 = tuning().n1_occupancy == 4;
+        if (S.min_sep) {
+            if (occ4) step_n1_kernel<true, 4><<<grid, kBlock, 0, st>>>(P, S, actions, out);
+            else step_n1_kernel<true, 3><<<grid, kBlock, 0, st>>>(P, S, actions, out);
+        } else {
+            if (occ4) step_n1_kernel<false, 4><<<grid, kBlock, 0, st>>>(P, S, actions, out);
+            else step_n1_kernel<false, 3><<<grid, kBlock, 0, st>>>(P, S, actions, out);
+        }
+    } else if (tuning().force_loop) {
         if (S.min_sep) step_loop_kernel<true><<<grid, kBlock, 0, st>>>(P, S, actions, out);
         else step_loop_kernel<false><<<grid, kBlock, 0, st>>>(P, S, actions, out);
+    } else {
+        int rc = 0;
+        switch (tiled_group(P.n_traffic)) {
+            case 1: rc = launch_tiled<1>(P, S, actions, out, st); break;
+            case 2: rc = launch_tiled<2>(P, S, actions, out, st); break;
+            case 4: rc = launch_tiled<4>(P, S, actions, out, st); break;
+            case 8: rc = launch_tiled<8>(P, S, actions, out, st); break;
+            case 16: rc = launch_tiled<16>(P, S, actions, out, st); break;
+            default: rc = launch_tiled<32>(P, S, actions, out, st); break;
+        }
+        if (rc) return rc;
     }
     return finish_launch();
 }
@@ -321,5 +590,12 @@ int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed, uint6
 }
 
 int64_t acas2d_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop)
+{
+    if (n1_occupancy == 3 || n1_occupancy == 4) tuning().n1_occupancy = n1_occupancy;
+    if (force_loop >= 0) tuning().force_loop = force_loop != 0;
+    return 0;
+}
 
 }  // extern "C"

@@ -27,10 +27,11 @@ STAT_SLOTS, STAT_FIELDS = 128, 16
 STAT_NAMES = ("episodes", "goal", "collision", "timeout", "length_sum", "return_fx", "min_sep_fx")
 STAT_FX_SCALE = 1048576.0
 FLAG_COLLISION, FLAG_GOAL, FLAG_TIMEOUT, FLAG_DONE, FLAG_OOB = 1, 2, 4, 8, 16
+STEPS_RESIDUAL_BIT = 0x40000000
 
 EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
-           "acas2d_launch_count")
+           "acas2d_launch_count", "acas2d_set_tuning")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -50,8 +51,7 @@ class State(ctypes.Structure):
     """``acas2d_state``: device pointers owned by the caller."""
     _fields_ = [("num_envs", ctypes.c_int64),
                 ("ppos", ctypes.c_void_p), ("paux", ctypes.c_void_p),
-                ("tpos0", ctypes.c_void_p), ("tvel", ctypes.c_void_p),
-                ("tpsi", ctypes.c_void_p), ("tvair", ctypes.c_void_p),
+                ("thot", ctypes.c_void_p), ("tres", ctypes.c_void_p),
                 ("episode_idx", ctypes.c_void_p), ("min_sep", ctypes.c_void_p),
                 ("stats", ctypes.c_void_p),
                 ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_uint64)]
@@ -91,6 +91,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_random_actions.argtypes = [SP, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
     lib.acas2d_launch_count.argtypes = []
     lib.acas2d_launch_count.restype = ctypes.c_int64
+    lib.acas2d_set_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]
     return lib
 
 

@@ -68,10 +68,8 @@ class BatchedACAS2D:
             # ---- state (layout: include/acas2d_b200.h)
             self.ppos = torch.zeros(B, 2, dtype=f64, device=dev)
             self.paux = torch.zeros(B, 2, dtype=f64, device=dev)          # 16 B records {psi, steps, ep_return}
-            self.tpos0 = torch.zeros(B, N, 2, dtype=f64, device=dev)
-            self.tvel = torch.zeros(B, N, 2, dtype=f64, device=dev)
-            self.tpsi = torch.zeros(B, N, dtype=f64, device=dev)
-            self.tvair = torch.ones(B, N, dtype=f64, device=dev)
+            self.thot = torch.zeros(B, N, 4, dtype=f32, device=dev)          # {x0, y0, psi, v}: all a step reads
+            self.tres = torch.zeros(B, N, 4, dtype=f64, device=dev)          # cold float64 remainders (injected states)
             self.episode_idx = torch.zeros(B, dtype=torch.int32, device=dev)
             self.min_sep = torch.zeros(B, dtype=f32, device=dev) if track_min_sep else None
             self.stats = torch.zeros(_native.STAT_SLOTS, _native.STAT_FIELDS, dtype=torch.int64, device=dev)
@@ -85,9 +83,8 @@ class BatchedACAS2D:
             self.ep_return = torch.zeros(B, dtype=f32, device=dev)
             self.ep_length = torch.zeros(B, dtype=torch.int32, device=dev)
         self._state = State(
-            num_envs=B, ppos=self.ppos.data_ptr(), paux=self.paux.data_ptr(), tpos0=self.tpos0.data_ptr(),
-            tvel=self.tvel.data_ptr(), tpsi=self.tpsi.data_ptr(), tvair=self.tvair.data_ptr(),
-            episode_idx=self.episode_idx.data_ptr(),
+            num_envs=B, ppos=self.ppos.data_ptr(), paux=self.paux.data_ptr(), thot=self.thot.data_ptr(),
+            tres=self.tres.data_ptr(), episode_idx=self.episode_idx.data_ptr(),
             min_sep=self.min_sep.data_ptr() if track_min_sep else None,
             stats=self.stats.data_ptr(), seed=self.seed, env_id_offset=self.env_id_offset)
         self._aux_full = StepAux(flags=self.flags.data_ptr(), outcome=self.outcome.data_ptr(),
@@ -248,7 +245,7 @@ class BatchedACAS2D:
             out["min_sep"] = self.min_sep.cpu().numpy()
         return out
 
-    _STATE_TENSORS = ("ppos", "paux", "tpos0", "tvel", "tpsi", "tvair", "episode_idx", "stats")
+    _STATE_TENSORS = ("ppos", "paux", "thot", "tres", "episode_idx", "stats")
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Checkpoint of the env batch (the reference never saves env state)."""

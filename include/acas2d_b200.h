@@ -24,14 +24,16 @@
  *   ppos        double[B][2]    player x, y                    (aircraft.py:9-10)
  *   paux        16 B / env      { double psi; int32 steps; float ep_return }
  *                               psi in degrees (aircraft.py:12); steps == game.steps
- *                               (game.py:30,197); ep_return == game.total_reward so far
- *                               (game.py:32,287)
- *   tpos0       double[B][N][2] intruder position at steps == 1 (closed-form origin)
- *   tvel        double[B][N][2] intruder displacement per step v*cos(psi)*dt, v*sin(psi)*dt;
- *                               position after k moves = tpos0 + k * tvel (straight line,
- *                               game.py:243-245; a_lat is always 0)
- *   tpsi, tvair double[B][N]    intruder heading [deg] / speed: cold, touched by
- *                               reset / inject / extract (tvair also by step when speeds differ, Q3)
+ *                               (game.py:30,197) | ACAS2D_STEPS_RESIDUAL_BIT; ep_return ==
+ *                               game.total_reward so far (game.py:32,287)
+ *   thot        float[B][N][4]  intruder record {x0, y0, psi, v}: position at steps == 1, heading [deg],
+ *                               speed.  The intruder flies a straight line (game.py:243-245, a_lat is
+ *                               always 0): position after k moves = (x0, y0) + k * v*dt*(cos psi, sin psi),
+ *                               evaluated in float64.  Spawned intruders are float32-representable by
+ *                               construction, so this 16-byte record is exact and is all a step reads.
+ *   tres        double[B][N][4] full - float32(full) of the same four values.  Cold: written by
+ *                               acas2d_inject_state, read by step / extract only for envs whose
+ *                               paux.steps carries ACAS2D_STEPS_RESIDUAL_BIT (injected float64 states).
  *   episode_idx uint32[B]       episodes started by this env (Philox counter word 2)
  *   min_sep     float[B]        running minimum separation of the episode, or NULL
  *   stats       int64[ACAS2D_STAT_SLOTS][ACAS2D_STAT_FIELDS]  finished-episode counters
@@ -53,6 +55,9 @@ extern "C" {
 #define ACAS2D_E_NO_DEVICE   (-4)  /* no CUDA device / not an sm_100 device */
 
 #define ACAS2D_MAX_TRAFFIC 1024
+
+/* bit of paux.steps: this env's intruder records need their float64 residuals (tres) */
+#define ACAS2D_STEPS_RESIDUAL_BIT 0x40000000
 
 /* step flags (uint8 per env) */
 #define ACAS2D_FLAG_COLLISION 1u   /* game.py:185-189  d < 2*COLLISION_RADIUS for any intruder */
@@ -109,10 +114,8 @@ typedef struct acas2d_state {
     int64_t   num_envs;
     void     *ppos;
     void     *paux;
-    void     *tpos0;
-    void     *tvel;
-    double   *tpsi;
-    double   *tvair;
+    void     *thot;
+    void     *tres;
     uint32_t *episode_idx;
     float    *min_sep;        /* optional */
     int64_t  *stats;          /* optional */
@@ -187,6 +190,13 @@ int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed,
 
 /* Kernels launched by this library since load (all entry points). */
 int64_t acas2d_launch_count(void);
+
+/* Experiment knobs (process-wide; also settable through the environment variables
+ * ACAS2D_N1_OCC and ACAS2D_FORCE_LOOP before the first call).  n1_occupancy: 3 or 4 resident
+ * blocks per SM for the N_TRAFFIC == 1 kernel (other values: unchanged).  force_loop: 1 routes
+ * N_TRAFFIC > 1 to the one-thread-per-env kernel that the shared-memory tiled kernel is
+ * checked against, 0 back to the tiled kernel, negative: unchanged. */
+int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop);
 
 #ifdef __cplusplus
 }

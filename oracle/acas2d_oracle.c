@@ -453,6 +453,8 @@ static void spawn_one(const acas2d_oracle_params *P, int N, uint64_t seed, uint6
         traffic[4 * i + 2] = (fmin + (fmax - fmin) * u01(r[2])) * P->airspeed;         /* :112 */
         traffic[4 * i + 3] = 0.0 + (360.0 - 0.0) * u01(r[3]);                           /* :114 */
     }
+    /* the new framework stores a spawned intruder as four float32 values (DESIGN.md "Data layout") */
+    for (int q = 0; q < 4 * N; ++q) traffic[q] = (double)(float)traffic[q];
 }
 
 void acas2d_oracle_spawn_philox(const acas2d_oracle_params *P, int64_t B, int N,

@@ -51,8 +51,7 @@ class HostBatch:
         self.variant = (0 if N == 1 else 1) if variant is None else variant
         f8, f4 = np.float64, np.float32
         self.ppos = np.zeros((B, 2), f8); self.paux = np.zeros((B, 2), f8)
-        self.tpos0 = np.zeros((B, N, 2), f8); self.tvel = np.zeros((B, N, 2), f8)
-        self.tpsi = np.zeros((B, N), f8); self.tvair = np.ones((B, N), f8)
+        self.thot = np.zeros((B, N, 4), f4); self.tres = np.zeros((B, N, 4), f8)
         self.episode_idx = np.zeros(B, np.uint32)
         self.min_sep = np.zeros(B, f4) if track_min_sep else None
         self.stats = np.zeros((_native.STAT_SLOTS, _native.STAT_FIELDS), np.int64)
@@ -60,9 +59,8 @@ class HostBatch:
         self.done = np.zeros(B, np.uint8); self.flags = np.zeros(B, np.uint8); self.outcome = np.zeros(B, np.uint8)
         self.term_obs = np.full((B, self.obs_dim), np.nan, f4); self.ep_return = np.zeros(B, f4)
         self.ep_length = np.zeros(B, np.int32)
-        self._state = State(num_envs=B, ppos=_p(self.ppos), paux=_p(self.paux), tpos0=_p(self.tpos0),
-                            tvel=_p(self.tvel), tpsi=_p(self.tpsi), tvair=_p(self.tvair),
-                            episode_idx=_p(self.episode_idx), min_sep=_p(self.min_sep), stats=_p(self.stats),
+        self._state = State(num_envs=B, ppos=_p(self.ppos), paux=_p(self.paux), thot=_p(self.thot),
+                            tres=_p(self.tres), episode_idx=_p(self.episode_idx), min_sep=_p(self.min_sep), stats=_p(self.stats),
                             seed=seed, env_id_offset=env_id_offset)
         self._aux = StepAux(flags=_p(self.flags), outcome=_p(self.outcome), term_obs=_p(self.term_obs),
                             ep_return=_p(self.ep_return), ep_length=_p(self.ep_length))
