@@ -230,6 +230,7 @@ def run_ours(args):
     lib = _native.load()
     if args.n1_occ:
         lib.acas2d_set_tuning(args.n1_occ, -1)
+    lib.acas2d_set_n1_kernel(args.n1_tma, args.n1_stages)
 
     env = BatchedACAS2D(B, n_traffic=N, device=dev, seed=13, env_id_offset=offset, auto_reset=True)
     env.reset()
@@ -336,6 +337,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true")
     ap.add_argument("--n1-occ", type=int, default=0, help="experiment: 3|4 resident blocks/SM for the N=1 kernel")
+    ap.add_argument("--n1-tma", type=int, default=-1, help="experiment: 1 = TMA-ring persistent kernel, 0 = direct kernel")
+    ap.add_argument("--n1-stages", type=int, default=0, help="experiment: TMA ring depth 2..5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,7 +52,7 @@ int finish_launch()
 
 // Tuning knobs for experiments (read once): ACAS2D_N1_OCC = 3|4 blocks/SM for the N == 1 kernel,
 // ACAS2D_FORCE_LOOP = 1 routes N > 1 to the simple per-thread kernel the tiled one is checked against.
-struct Tuning { int n1_occupancy; bool force_loop; };
+struct Tuning { int n1_occupancy; bool force_loop; int n1_tma; int n1_stages; };
 Tuning &tuning()
 {
     static Tuning t = [] {
@@ -61,6 +61,10 @@ Tuning &tuning()
         x.n1_occupancy = (o && std::atoi(o) == 3) ? 3 : 4;
         const char *f = std::getenv("ACAS2D_FORCE_LOOP");
         x.force_loop = f && std::atoi(f) != 0;
+        const char *t = std::getenv("ACAS2D_N1_TMA");
+        x.n1_tma = t ? std::atoi(t) : 1;
+        const char *g = std::getenv("ACAS2D_N1_STAGES");
+        x.n1_stages = g ? std::atoi(g) : 3;
         return x;
     }();
     return t;
@@ -116,6 +120,149 @@ step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ a
         store_env1(S, i, e, MINSEP);
     }
     tally_flush_warp(S.stats, tally);
+}
+
+// ---------------------------------------------------------------- N_TRAFFIC == 1, persistent + TMA ring
+// The direct kernel above is bound by load latency: every warp sits on its five loads
+// (long-scoreboard stall, profiles/r01_ncu_step_n1_v1_full.csv) before a ~400-instruction FP64
+// dependency chain, and registers cap residency at 8 warps per scheduler.  Here the loads are taken
+// off the warps: one elected thread per CTA keeps a STAGES-deep ring of 256-env input tiles in
+// flight with TMA bulk copies (cp.async.bulk.shared.global, completion on an mbarrier with
+// expect_tx), the CTA is persistent (grid = SMs x resident CTAs) and walks tiles round-robin; all
+// 256 threads only compute out of shared memory and stream their results straight from registers
+// (128-bit streaming stores).  Bytes in flight per SM = OCC x STAGES x 13 KB, independent of how
+// many warps are stalled on arithmetic.
+constexpr int kTileEnvs = kBlock;
+constexpr int kStageBytes = kTileEnvs * (16 + 16 + 16 + 4);          // ppos | paux | thot | action
+constexpr int kOffPaux = kTileEnvs * 16, kOffThot = kTileEnvs * 32, kOffAct = kTileEnvs * 48;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int STAGES, int OCC>
+__global__ void __launch_bounds__(kBlock, OCC)
+step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
+                   const long long full_tiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](long long tile, int s) {
+        unsigned char *base = smem + s * kStageBytes;
+        const long long e0 = tile * kTileEnvs;
+        mbar_expect_tx(&full[s], kStageBytes);
+        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, &full[s]);
+        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, &full[s]);
+        tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, &full[s]);
+        tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, &full[s]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (tile < full_tiles) issue(tile, s);
+        }
+    }
+
+    Tally tally;
+    tally_clear(tally);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (unsigned)(it / STAGES) & 1u);
+        const unsigned char *base = smem + s * kStageBytes;
+        const Vec2d pp = ((const Vec2d *)base)[tid];
+        const PlayerAux pa = ((const PlayerAux *)(base + kOffPaux))[tid];
+        const Float4 h = ((const Float4 *)(base + kOffThot))[tid];
+        const float a = ((const float *)(base + kOffAct))[tid];
+        __syncthreads();                                   // every thread has drained stage s
+        if (tid == 0) {
+            const long long next = tile + (long long)STAGES * gridDim.x;
+            if (next < full_tiles) issue(next, s);
+        }
+        const int64_t i = tile * kTileEnvs + tid;
+        Env1 e;
+        e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.ret = pa.ep_return;
+        e.steps = pa.steps & kStepsMask;
+        e.residual = (pa.steps & kResidualBit) != 0;
+        e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
+        if (e.residual) {
+            const Residual r = S.tres[i];
+            e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
+        }
+        e.minsep = 0.0f;
+        e.respawned = false;
+        step_env1<false, true>(P, S, e, a, i, out, tally, nullptr);
+        store_env1(S, i, e, false);
+    }
+
+    // ragged tail (B % 256 envs): one CTA, plain loads
+    const int64_t tail0 = (int64_t)full_tiles * kTileEnvs;
+    if (tail0 < S.B && blockIdx.x == (unsigned)(full_tiles % gridDim.x)) {
+        const int64_t i = tail0 + tid;
+        if (i < S.B) {
+            Env1 e;
+            load_env1(S, i, e, false);
+            step_env1<false, true>(P, S, e, __ldcs(actions + i), i, out, tally, nullptr);
+            store_env1(S, i, e, false);
+        }
+    }
+    tally_flush_warp(S.stats, tally);
+}
+
+template <int STAGES, int OCC>
+int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             STAGES * kStageBytes + 64);
+    }
+    const long long full_tiles = S.B / kTileEnvs;
+    long long grid = (long long)sms * OCC;
+    const long long tiles = full_tiles + ((S.B % kTileEnvs) ? 1 : 0);
+    if (grid > tiles) grid = tiles;
+    step_n1_tma_kernel<STAGES, OCC><<<(unsigned)grid, kBlock, STAGES * kStageBytes + 64, st>>>(P, S, actions, out, full_tiles);
+    return 0;
 }
 
 template <bool MINSEP>
@@ -497,7 +644,20 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (P.n_traffic == 1) {
         const bool occ4 = tuning().n1_occupancy == 4;
-        if (S.min_sep) {
+        const bool aligned = (((uintptr_t)actions | (uintptr_t)S.ppos | (uintptr_t)S.paux | (uintptr_t)S.thot) & 15) == 0;
+        if (!S.min_sep && tuning().n1_tma && aligned) {
+            const int stages = tuning().n1_stages;
+            if (occ4) {
+                if (stages <= 2) launch_n1_tma<2, 4>(P, S, actions, out, st);
+                else if (stages == 3) launch_n1_tma<3, 4>(P, S, actions, out, st);
+                else launch_n1_tma<4, 4>(P, S, actions, out, st);
+            } else {
+                if (stages <= 2) launch_n1_tma<2, 3>(P, S, actions, out, st);
+                else if (stages == 3) launch_n1_tma<3, 3>(P, S, actions, out, st);
+                else if (stages == 4) launch_n1_tma<4, 3>(P, S, actions, out, st);
+                else launch_n1_tma<5, 3>(P, S, actions, out, st);
+            }
+        } else if (S.min_sep) {
             if (occ4) step_n1_kernel<true, 4><<<grid, kBlock, 0, st>>>(P, S, actions, out);
             else step_n1_kernel<true, 3><<<grid, kBlock, 0, st>>>(P, S, actions, out);
         } else {
@@ -595,6 +755,13 @@ int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop)
 {
     if (n1_occupancy == 3 || n1_occupancy == 4) tuning().n1_occupancy = n1_occupancy;
     if (force_loop >= 0) tuning().force_loop = force_loop != 0;
+    return 0;
+}
+
+int acas2d_set_n1_kernel(int32_t use_tma, int32_t stages)
+{
+    if (use_tma >= 0) tuning().n1_tma = use_tma != 0;
+    if (stages >= 2 && stages <= 5) tuning().n1_stages = stages;
     return 0;
 }
 

@@ -31,7 +31,7 @@ STEPS_RESIDUAL_BIT = 0x40000000
 
 EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
-           "acas2d_launch_count", "acas2d_set_tuning")
+           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -92,6 +92,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_launch_count.argtypes = []
     lib.acas2d_launch_count.restype = ctypes.c_int64
     lib.acas2d_set_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    lib.acas2d_set_n1_kernel.argtypes = [ctypes.c_int32, ctypes.c_int32]
     return lib
 
 

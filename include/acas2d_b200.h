@@ -198,6 +198,11 @@ int64_t acas2d_launch_count(void);
  * checked against, 0 back to the tiled kernel, negative: unchanged. */
 int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop);
 
+/* N_TRAFFIC == 1 kernel choice (process-wide; env ACAS2D_N1_TMA / ACAS2D_N1_STAGES): use_tma 1 = the
+ * persistent kernel fed by a TMA bulk-copy ring of `stages` (2..5) input tiles (default), 0 = the
+ * direct one-thread-per-env kernel, negative = unchanged.  Both are bit-identical in results. */
+int acas2d_set_n1_kernel(int32_t use_tma, int32_t stages);
+
 #ifdef __cplusplus
 }
 #endif

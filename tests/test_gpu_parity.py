@@ -185,6 +185,39 @@ def test_tiled_kernel_equals_loop_kernel(cuda, n):
     assert torch.equal(a.episode_counters(), b.episode_counters())
 
 
+@pytest.mark.parametrize("stages,occ", [(2, 4), (3, 4), (4, 3), (5, 3)])
+def test_tma_ring_kernel_equals_direct_kernel(cuda, stages, occ):
+    """N_TRAFFIC == 1: the persistent kernel fed by the TMA bulk-copy ring and the direct
+    one-thread-per-env kernel are the same function, bit for bit -- ragged batch (B % 256 != 0),
+    injected float64 states (residual path) and auto-resets included."""
+    from gym_ACAS2D.envs import _native
+    lib = _native.load()
+    B = 148 * 4 * 256 * 2 + 256 * 3 + 77          # several tiles per CTA, then a ragged tail
+    a = make(B, 1, seed=4, auto_reset=True); b = make(B, 1, seed=4, auto_reset=True)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    for e in (a, b):
+        ex = e.extract_state()
+        ex["steps"][:] = 1 + (np.arange(B) % 1000)
+        ex["traffic"][::3, 0, 0] += 0.123456789        # not float32-representable -> residual path
+        e.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    try:
+        for t in range(30):
+            act = a.random_actions(t, 9)
+            lib.acas2d_set_tuning(occ, -1); lib.acas2d_set_n1_kernel(1, stages)
+            oa, ra, da = a.step(act)
+            lib.acas2d_set_n1_kernel(0, 0)
+            ob, rb, db = b.step(act)
+            assert torch.equal(oa.view(torch.int32), ob.view(torch.int32))
+            assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(a.flags, b.flags)
+            assert torch.equal(a.term_obs[da], b.term_obs[db]) and torch.equal(a.ep_length[da], b.ep_length[db])
+    finally:
+        lib.acas2d_set_tuning(4, -1); lib.acas2d_set_n1_kernel(1, 3)
+    assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.thot, b.thot)
+    assert torch.equal(a.episode_idx, b.episode_idx) and torch.equal(a.episode_counters(), b.episode_counters())
+    assert a.episode_counters()[0].item() > 1000
+
+
 def test_sharding_invariance_and_determinism(cuda):
     """1 Mi envs (BASELINE config 3 size): two half-batches addressed by global env id reproduce the
     full batch bit for bit (state, outputs, integer episode counters) -- the multi-GPU property."""
