@@ -82,6 +82,7 @@ inline DevParams make_dev_params(const acas2d_params &p)
     d.tn_x_span = p.width - p.aircraft_size;                        // game.py:109
     d.tn_y_span = 3.0 * p.height / 5.0;                             // game.py:110
     d.inv_max_steps = (float)(1.0 / p.max_steps);
+    d.inv_d_dev_max_f = (float)(1.0 / p.d_dev_max);
     d.inv_d_goal_max = (float)(1.0 / p.d_goal_max);
     d.inv_d_sep_max = (float)(1.0 / p.d_separation_max);
     d.inv_d_cpa_max = (float)(1.0 / p.d_cpa_max);
@@ -235,7 +236,7 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
     Intruder t = intruder_at(P, e.tr, k);                                  // game.py:243-245
     if (MINSEP) {                                                          // game.py:237 (Q10: old traffic)
         const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
-        e.minsep = fminf(e.minsep, sqrtf((float)(ox * ox + oy * oy)));
+        e.minsep = fminf(e.minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
     }
 
     // ---- game.observe / evaluate / is_done (game.py:194-314)
@@ -356,7 +357,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
         const Intruder t = intruder_at(P, traffic_load(S, i * N + j, residual), k);
         if (MINSEP) {
             const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
-            minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
+            minsep = fminf(minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
         }
         const Encounter en = encounter(P, p, t);
         if (j == 0) e0 = en;

@@ -143,14 +143,13 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+__device__ __forceinline__ void mbar_wait(uint32_t addr, unsigned parity)
 {
-    const uint32_t addr = smem_u32(bar);
     uint32_t ok;
     do {
         asm volatile("{\n\t.reg .pred p;\n\t"
@@ -161,10 +160,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 }
 
 // 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gmem_src, unsigned bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 
 template <int STAGES, int OCC>
@@ -182,14 +181,15 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
     }
     __syncthreads();
 
+    const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full);
     auto issue = [&](long long tile, int s) {
-        unsigned char *base = smem + s * kStageBytes;
+        const uint32_t base = smem_base + s * kStageBytes, bar = full_base + 8 * s;
         const long long e0 = tile * kTileEnvs;
-        mbar_expect_tx(&full[s], kStageBytes);
-        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, &full[s]);
-        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, &full[s]);
-        tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, &full[s]);
-        tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, &full[s]);
+        mbar_expect_tx(bar, kStageBytes);
+        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, bar);
+        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, bar);
+        tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar);
+        tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, bar);
     };
 
     if (tid == 0) {
@@ -205,7 +205,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
     int it = 0;
     for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES;
-        mbar_wait(&full[s], (unsigned)(it / STAGES) & 1u);
+        mbar_wait(full_base + 8 * s, (unsigned)(it / STAGES) & 1u);
         const unsigned char *base = smem + s * kStageBytes;
         const Vec2d pp = ((const Vec2d *)base)[tid];
         const PlayerAux pa = ((const PlayerAux *)(base + kOffPaux))[tid];
@@ -222,7 +222,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         e.steps = pa.steps & kStepsMask;
         e.residual = (pa.steps & kResidualBit) != 0;
         e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
-        if (e.residual) {
+        if (__builtin_expect(e.residual, 0)) {
             const Residual r = S.tres[i];
             e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
         }
@@ -390,7 +390,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
             const Intruder t = intruder_at(P, tr, k);
             if (MINSEP) {
                 const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
-                minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
+                minsep = fminf(minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
             }
             const Encounter en = encounter(P, p, t);
             if (j == 0) e0 = en;
@@ -682,6 +682,32 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
     return finish_launch();
 }
 
+// Host-buffer step.  Large batches are cut into chunks that rotate over three internal streams so
+// that the PCIe H2D copy of chunk c+1, the kernel of chunk c and the D2H copies of chunk c-1
+// overlap (the D2H leg, 4L+5 bytes per env, is the bound); small batches use the caller's stream.
+namespace {
+struct HostPipe {
+    cudaStream_t s[3];
+    cudaEvent_t start, done[3];
+    bool ok = false;
+};
+HostPipe &host_pipe()
+{
+    static HostPipe p = [] {
+        HostPipe q;
+        q.ok = true;
+        for (int i = 0; i < 3; ++i) {
+            q.ok = q.ok && cudaStreamCreateWithFlags(&q.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            q.ok = q.ok && cudaEventCreateWithFlags(&q.done[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        q.ok = q.ok && cudaEventCreateWithFlags(&q.start, cudaEventDisableTiming) == cudaSuccess;
+        return q;
+    }();
+    return p;
+}
+constexpr int64_t kHostChunk = 256 * 1024;     // envs per chunk (multiple of the 256-env TMA tile)
+}  // namespace
+
 int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, const float *h_actions, float *h_obs,
                      float *h_reward, uint8_t *h_done, float *d_actions, float *d_obs, float *d_reward,
                      uint8_t *d_done, const acas2d_step_aux *aux, void *stream)
@@ -690,17 +716,55 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
     if (!h_actions || !h_obs || !h_reward || !h_done || !d_actions || !d_obs || !d_reward || !d_done)
         return ACAS2D_E_NULL;
     const int64_t B = state->num_envs;
-    const int L = 5 + 3 * params->n_traffic;
+    const int N = params->n_traffic, L = 5 + 3 * N;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, sizeof(float) * B, cudaMemcpyHostToDevice, st);
-    if (err != cudaSuccess) return (int)err;
-    if (int e = acas2d_step(params, state, d_actions, d_obs, d_reward, d_done, aux, stream)) return e;
-    err = cudaMemcpyAsync(h_obs, d_obs, sizeof(float) * B * L, cudaMemcpyDeviceToHost, st);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaMemcpyAsync(h_done, d_done, sizeof(uint8_t) * B, cudaMemcpyDeviceToHost, st);
-    if (err != cudaSuccess) return (int)err;
+    cudaError_t err;
+#define ACAS_TRY(call) do { err = (call); if (err != cudaSuccess) return (int)err; } while (0)
+    HostPipe *pipe = (B >= 2 * kHostChunk) ? &host_pipe() : nullptr;
+    if (!pipe || !pipe->ok) {
+        ACAS_TRY(cudaMemcpyAsync(d_actions, h_actions, sizeof(float) * B, cudaMemcpyHostToDevice, st));
+        if (int e = acas2d_step(params, state, d_actions, d_obs, d_reward, d_done, aux, stream)) return e;
+        ACAS_TRY(cudaMemcpyAsync(h_obs, d_obs, sizeof(float) * B * L, cudaMemcpyDeviceToHost, st));
+        ACAS_TRY(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+        ACAS_TRY(cudaMemcpyAsync(h_done, d_done, sizeof(uint8_t) * B, cudaMemcpyDeviceToHost, st));
+        return (int)cudaStreamSynchronize(st);
+    }
+    ACAS_TRY(cudaEventRecord(pipe->start, st));
+    for (int i = 0; i < 3; ++i) ACAS_TRY(cudaStreamWaitEvent(pipe->s[i], pipe->start, 0));
+    int c = 0;
+    for (int64_t off = 0; off < B; off += kHostChunk, ++c) {
+        const int64_t n = (B - off) < kHostChunk ? (B - off) : kHostChunk;
+        cudaStream_t cs = pipe->s[c % 3];
+        acas2d_state sub = *state;
+        sub.num_envs = n;
+        sub.ppos = (char *)state->ppos + 16 * off;
+        sub.paux = (char *)state->paux + 16 * off;
+        sub.thot = (char *)state->thot + 16 * N * off;
+        sub.tres = (char *)state->tres + 32 * N * off;
+        sub.episode_idx = state->episode_idx + off;
+        sub.min_sep = state->min_sep ? state->min_sep + off : nullptr;
+        sub.env_id_offset = state->env_id_offset + (uint64_t)off;
+        acas2d_step_aux sa = {};
+        if (aux) {
+            sa.flags = aux->flags ? aux->flags + off : nullptr;
+            sa.outcome = aux->outcome ? aux->outcome + off : nullptr;
+            sa.term_obs = aux->term_obs ? aux->term_obs + L * off : nullptr;
+            sa.ep_return = aux->ep_return ? aux->ep_return + off : nullptr;
+            sa.ep_length = aux->ep_length ? aux->ep_length + off : nullptr;
+        }
+        ACAS_TRY(cudaMemcpyAsync(d_actions + off, h_actions + off, sizeof(float) * n, cudaMemcpyHostToDevice, cs));
+        if (int e = acas2d_step(params, &sub, d_actions + off, d_obs + L * off, d_reward + off, d_done + off,
+                                aux ? &sa : nullptr, cs))
+            return e;
+        ACAS_TRY(cudaMemcpyAsync(h_obs + L * off, d_obs + L * off, sizeof(float) * n * L, cudaMemcpyDeviceToHost, cs));
+        ACAS_TRY(cudaMemcpyAsync(h_reward + off, d_reward + off, sizeof(float) * n, cudaMemcpyDeviceToHost, cs));
+        ACAS_TRY(cudaMemcpyAsync(h_done + off, d_done + off, sizeof(uint8_t) * n, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int i = 0; i < 3 && i < c; ++i) {
+        ACAS_TRY(cudaEventRecord(pipe->done[i], pipe->s[i]));
+        ACAS_TRY(cudaStreamWaitEvent(st, pipe->done[i], 0));
+    }
+#undef ACAS_TRY
     return (int)cudaStreamSynchronize(st);
 }
 

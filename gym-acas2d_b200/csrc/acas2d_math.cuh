@@ -47,7 +47,7 @@ struct DevParams {
     double goal_r2;         // GOAL_RADIUS^2, game.py:192
     double width, height;   // aircraft.py:28-29
     double inv_360;         // obs[1] = psi/360, game.py:200
-    double inv_d_dev_max;   // obs[2] = d_dev/d_dev_max, game.py:201
+    double inv_d_dev_max;   // 1/d_dev_max, game.py:201
     // ---- spawn (game.py:85-116)
     double dt, airspeed;
     double player_x0, player_y0, player_psi_base, player_heading_lim;
@@ -56,6 +56,7 @@ struct DevParams {
     double tn_x_span, tn_y_span;       // intruders n>0: U(0, WIDTH-SIZE) x U(0, 3*HEIGHT/5)
     // ---- float32 observation / reward block
     float inv_max_steps;    // obs[0], time discount (game.py:199,262)
+    float inv_d_dev_max_f;  // obs[2] = d_dev/d_dev_max, game.py:201
     float inv_d_goal_max;   // obs[3], game.py:202
     float inv_d_sep_max;    // game.py:208
     float inv_d_cpa_max;    // game.py:209
@@ -75,12 +76,75 @@ static constexpr double kDeg2Rad = 0.017453292519943295;  // pi/180
 static constexpr float kTwoPiF = 6.283185307179586f;
 static constexpr float kInvTwoPiF = 0.15915494309189535f;
 
+// float32 special functions on the MUFU unit (one instruction each, <= 2 ulp).  Outputs of the
+// observation / reward block are float32 with stated tolerances >= 5e-7, so IEEE-exact sqrtf /
+// division (8-10 instructions plus a slow-path branch each) buy nothing here.
 ACAS_HD float acas_rsqrtf(float x)
 {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 #else
     return 1.0f / sqrtf(x);
+#endif
+}
+
+ACAS_HD float acas_sqrtf(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
+
+ACAS_HD float acas_rcpf(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// atan2(y, x) mod 2*pi expressed in TURNS, [0, 1] (kinematics.py:16-22 divided by 360).
+// Octant reduction + degree-7 minimax polynomial in t^2 for atan(t)/(2 pi), t in [0,1]:
+// max error 3.2e-8 turns evaluated in float32 (fit: near-minimax Chebyshev, checked on 2e5 points).
+// A tiny negative y gives 1.0 exactly like the reference's (atan2 % 2pi) -> 360 degrees.
+ACAS_HD float atan2_turns(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = mn * acas_rcpf(mx);
+    t = (mx > 0.0f) ? t : 0.0f;                       // atan2(0, 0) == 0
+    const float z = t * t;
+    float p = -0.0007430583355017006f;
+    p = fmaf(p, z, 0.0038461685180664062f);
+    p = fmaf(p, z, -0.009448567405343056f);
+    p = fmaf(p, z, 0.015766043215990067f);
+    p = fmaf(p, z, -0.022308088839054108f);
+    p = fmaf(p, z, 0.03178202360868454f);
+    p = fmaf(p, z, -0.05304946005344391f);
+    p = fmaf(p, z, 0.15915492177009583f);
+    float a = p * t;                                  // [0, 1/8]
+    a = (ay > ax) ? 0.25f - a : a;
+    a = (x < 0.0f) ? 0.5f - a : a;
+    a = (y < 0.0f) ? 1.0f - a : a;
+    return a;
+}
+
+// v with its sign flipped when bit 0 of `flip` is set (integer op on the high word).
+ACAS_HD double flip_sign(double v, int flip)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (flip << 31), __double2loint(v));
+#else
+    return (flip & 1) ? -v : v;
 #endif
 }
 
@@ -119,23 +183,27 @@ ACAS_HD void sincos_deg(double deg, double *s, double *c)
     pc = fma(pc, z, -1.38888888888741095749e-03);
     pc = fma(pc, z, 4.16666666666666019037e-02);
     const double cs = 1.0 - (0.5 * z - z * z * pc);
-    const double a = (q & 1) ? cs : sn, b = (q & 1) ? sn : cs;
-    *s = (q & 2) ? -a : a;
-    *c = ((q + 1) & 2) ? -b : b;
+    const bool odd = (q & 1) != 0;
+    const double a = odd ? cs : sn, b = odd ? sn : cs;
+    *s = flip_sign(a, (q >> 1) & 1);
+    *c = flip_sign(b, ((q + 1) >> 1) & 1);
 }
 
 // Python float `%` with divisor 360 (aircraft.py:22, kinematics.py:58,68, game.py:92,106):
 // result in [0, 360], equal to 360.0 only when a tiny negative value rounds up.
-ACAS_HD double wrap360(double t)
+ACAS_HD double wrap360_slow(double t)
 {
-    if (t >= 0.0) {
-        if (t < 360.0) return t;
-        if (t < 720.0) return t - 360.0;      // exact, == fmod
-    } else if (t >= -360.0) {
-        return t + 360.0;                      // fmod(t,360) == t, then + 360
-    }
     double r = fmod(t, 360.0);
     if (r != 0.0) { if (r < 0.0) r += 360.0; } else { r = 0.0; }
+    return r;
+}
+
+ACAS_HD double wrap360(double t)
+{
+    const bool hi = t >= 360.0, lo = t < 0.0;
+    double r = hi ? t - 360.0 : (lo ? t + 360.0 : t);     // exact where fmod is (|t| < 720 resp. >= -360)
+    const bool ok = hi ? (r < 360.0) : (lo ? (t >= -360.0) : true);
+    if (!ok) r = wrap360_slow(t);                          // |heading step| > 360 deg: unclipped actions only
     return r;
 }
 
@@ -235,7 +303,7 @@ ACAS_HD Encounter encounter(const DevParams &P, const Player &p, const Intruder 
     const double q2 = qx * qx + qy * qy;
     const double dot = ex * qx + ey * qy;
 
-    e.d = sqrtf((float)e.d2);
+    e.d = acas_sqrtf((float)e.d2);
     const float cr = (float)cross * acas_rsqrtf((float)w2);
     e.d_cpa = (wx < 0.0) ? -cr : cr;
     e.v_c = (float)dot * acas_rsqrtf((float)q2);          // displacement units; * FPS = px/s (Q4)
@@ -255,17 +323,16 @@ ACAS_HD PlayerView player_view(const DevParams &P, const Player &p, int32_t step
     PlayerView v;
     const double gx = P.goal_x - p.x, gy = P.goal_y - p.y;
     v.dg2 = gx * gx + gy * gy;
-    v.d_goal = sqrtf((float)v.dg2);
-    // heading_to_goal (game.py:171-173, kinematics.py:16-22): degrees(atan2 mod 2pi)
-    float phi = atan2f((float)gy, (float)gx);
-    if (phi < 0.0f) phi += kTwoPiF;
-    const float phi_turns = phi * kInvTwoPiF;
+    v.d_goal = acas_sqrtf((float)v.dg2);
+    // heading_to_goal (game.py:171-173, kinematics.py:16-22): degrees(atan2 mod 2pi) = 360 * turns
+    const float gyf = (float)gy;
+    const float phi_turns = atan2_turns(gyf, (float)gx);
     v.phi_deg = phi_turns * 360.0f;
     // plan_deviation (game.py:175-180) = d_goal*sin(heading_to_goal) == goal_y - y
-    v.d_dev = (float)gy;
+    v.d_dev = gyf;
     v.obs[0] = (float)steps * P.inv_max_steps;
     v.obs[1] = (float)(p.psi * P.inv_360);
-    v.obs[2] = (float)(gy * P.inv_d_dev_max);
+    v.obs[2] = gyf * P.inv_d_dev_max_f;
     v.obs[3] = v.d_goal * P.inv_d_goal_max;
     v.obs[4] = phi_turns;
     return v;
@@ -275,24 +342,23 @@ ACAS_HD PlayerView player_view(const DevParams &P, const Player &p, int32_t step
 ACAS_HD float shaped_reward(const DevParams &P, const Player &p, const PlayerView &v,
                             const Encounter &e0, int32_t steps)
 {
-    // delta_heading (kinematics.py:82-83); psi - phi formed in float64 before rounding
-    const float a = fabsf((float)(p.psi - (double)v.phi_deg));
+    (void)p;
+    // delta_heading (kinematics.py:82-83) from the float32 heading / bearing (error < 5e-5 deg)
+    const float a = fabsf(v.obs[1] * 360.0f - v.phi_deg);
     const float dh = fminf(a, 360.0f - a);
     float h = 1.0f - dh * (1.0f / 180.0f);
-    h = h * h; h = h * h;                                   // rewards.py:7
-    float r;
-    if (e0.v_c <= 0.0f) {                                    // rewards.py:54 (NaN -> else, as in Python)
-        float c = e0.d_cpa * P.inv_safe_distance;            // rewards.py:16
-        c = c * c; c = c * c;
-        c = fminf(1.0f, c);                                  // min(1, nan) == 1 in Python, fminf agrees
-        const float ad = fabsf(v.d_dev);                     // rewards.py:21-27
-        const float dv = (ad > P.rw_dev_max) ? 0.0f : sqrtf(fmaxf(0.0f, 1.0f - ad * P.inv_rw_dev_max));
-        r = h * c * dv;
-    } else {
-        float g = 1.0f - v.d_goal * P.inv_rw_goal_max;       // rewards.py:48
-        g = g * g; g = g * g;
-        r = h * fminf(1.0f, g);
-    }
+    h = h * h; h = h * h;                                    // rewards.py:7
+    // v_closing <= 0 branch (rewards.py:55-57)
+    float c = e0.d_cpa * P.inv_safe_distance;                // rewards.py:16
+    c = c * c; c = c * c;
+    c = fminf(1.0f, c);                                      // min(1, nan) == 1 in Python, fminf agrees
+    const float ad = fabsf(v.d_dev);                         // rewards.py:21-27: 0 beyond d_dev_max
+    const float dv = acas_sqrtf(fmaxf(0.0f, 1.0f - ad * P.inv_rw_dev_max));
+    // else branch (rewards.py:59-60)
+    float g = 1.0f - v.d_goal * P.inv_rw_goal_max;           // rewards.py:48
+    g = g * g; g = g * g;
+    g = fminf(1.0f, g);
+    const float r = (e0.v_c <= 0.0f) ? h * c * dv : h * g;   // rewards.py:54 (NaN -> else, as in Python)
     return r * (1.0f - (float)steps * P.inv_max_steps);      // game.py:262-263
 }
 

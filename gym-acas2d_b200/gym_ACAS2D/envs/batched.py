@@ -148,10 +148,10 @@ class BatchedACAS2D:
         self.launches += 1
         return self.obs, self.reward, self.done
 
-    def step_host(self, actions: np.ndarray):
-        """Host-buffer step (the end-to-end path): ``actions`` float32[B] in host memory ->
-        (obs float32[B, L], reward float32[B], done bool[B]) numpy views of pinned buffers.
-        The H2D copy, the kernel, the three D2H copies and one stream sync happen inside the call."""
+    def host_buffers(self) -> Dict[str, np.ndarray]:
+        """Pinned host staging buffers of ``step_host`` as numpy views: ``actions`` float32[B] (write
+        your actions here and call ``step_host()`` to skip the pageable->pinned copy), ``obs``,
+        ``reward``, ``done``."""
         if self._host is None:
             B, L = self.num_envs, self.obs_dim
             self._host = dict(
@@ -160,15 +160,28 @@ class BatchedACAS2D:
                 reward=torch.zeros(B, dtype=torch.float32).pin_memory(),
                 done=torch.zeros(B, dtype=torch.uint8).pin_memory())
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
+        return self._host_np
+
+    def step_host(self, actions: Optional[np.ndarray] = None):
+        """Host-buffer step (the end-to-end path): ``actions`` float32[B] in host memory (``None`` =
+        already written into ``host_buffers()["actions"]``) -> (obs float32[B, L], reward float32[B],
+        done bool[B]) numpy views of pinned buffers.  The H2D copy, the kernel, the three D2H copies
+        and one stream sync happen inside the call (chunk-pipelined over streams for large batches)."""
+        hb = self.host_buffers()
         h = self._host
-        np.copyto(self._host_np["actions"], np.asarray(actions, dtype=np.float32).reshape(-1))
+        a_ptr = h["actions"].data_ptr()
+        if isinstance(actions, torch.Tensor) and actions.device.type == "cpu" and actions.is_pinned() \
+                and actions.dtype == torch.float32 and actions.is_contiguous() and actions.numel() == self.num_envs:
+            a_ptr = actions.data_ptr()                      # caller-owned pinned memory: no staging copy
+        elif actions is not None:
+            np.copyto(hb["actions"], np.asarray(actions, dtype=np.float32).reshape(-1))
         with torch.cuda.device(self.device):
             _native.check(self.lib.acas2d_step_host(
-                self._p(), self._s(), h["actions"].data_ptr(), h["obs"].data_ptr(), h["reward"].data_ptr(),
+                self._p(), self._s(), a_ptr, h["obs"].data_ptr(), h["reward"].data_ptr(),
                 h["done"].data_ptr(), self._actions_dev.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
                 self.done_u8.data_ptr(), ctypes.byref(self._aux_full), self._stream()), "acas2d_step_host")
         self.launches += 1
-        return self._host_np["obs"], self._host_np["reward"], self._host_np["done"].view(np.bool_)
+        return hb["obs"], hb["reward"], hb["done"].view(np.bool_)
 
     # ------------------------------------------------------------------ synthetic rollouts
     def random_actions(self, step_index: int, action_seed: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -190,21 +203,26 @@ class BatchedACAS2D:
                 reward_sum.data_ptr() if reward_sum is not None else None, self._stream()), "acas2d_rollout_random")
         self.launches += 1
 
-    def capture_steps(self, actions: torch.Tensor, full_outputs: bool = False) -> "torch.cuda.CUDAGraph":
-        """Capture ``len(actions)`` consecutive steps (actions [K, B] resident in HBM) into one
-        CUDA graph; replay with ``graph.replay()``.  Launch-bound batches need this."""
+    def capture_steps(self, actions: torch.Tensor, full_outputs: bool = False, num_steps: Optional[int] = None,
+                      warmup: bool = True) -> "torch.cuda.CUDAGraph":
+        """Capture consecutive steps into one CUDA graph (replay with ``graph.replay()``): step k uses
+        ``actions[k % len(actions)]`` (actions [K, B], resident in HBM), ``num_steps`` steps in total
+        (default K).  Launch-bound batches and host-overhead-free rollouts need this.  With ``warmup``
+        one eager step with ``actions[0]`` runs first (kernels must be loaded before capture)."""
         actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         assert actions.dim() == 2 and actions.shape[1] == self.num_envs
         self._graph_actions = actions
+        n = int(num_steps or actions.shape[0])
         stream = torch.cuda.Stream(self.device)
         stream.wait_stream(torch.cuda.current_stream(self.device))
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.stream(stream):
-            self.step(actions[0], full_outputs)                      # warm-up outside capture
+            if warmup:
+                self.step(actions[0], full_outputs)
             torch.cuda.current_stream(self.device).synchronize()
             with torch.cuda.graph(graph, stream=stream):
-                for k in range(actions.shape[0]):
-                    self.step(actions[k], full_outputs)
+                for k in range(n):
+                    self.step(actions[k % actions.shape[0]], full_outputs)
         torch.cuda.current_stream(self.device).wait_stream(stream)
         return graph
 
