@@ -211,6 +211,11 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         const PlayerAux pa = ((const PlayerAux *)(base + kOffPaux))[tid];
         const Float4 h = ((const Float4 *)(base + kOffThot))[tid];
         const float a = ((const float *)(base + kOffAct))[tid];
+        // WAR across proxies: the generic-proxy shared loads above must have been performed before
+        // the async proxy (the TMA refill issued below) may overwrite the stage.  bar.sync alone does
+        // not order them -- a warp can pass the barrier with its LDS still queued, and the bulk copy
+        // does not go through that queue (observed: whole warps reading the NEXT tile's records).
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();                                   // every thread has drained stage s
         if (tid == 0) {
             const long long next = tile + (long long)STAGES * gridDim.x;

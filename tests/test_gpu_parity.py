@@ -218,6 +218,30 @@ def test_tma_ring_kernel_equals_direct_kernel(cuda, stages, occ):
     assert a.episode_counters()[0].item() > 1000
 
 
+@pytest.mark.parametrize("stages,occ", [(3, 4), (5, 3)])
+def test_tma_ring_stress_at_full_size(cuda, stages, occ):
+    """Regression for a cross-proxy WAR race: at 4 Mi envs every CTA refills each ring stage ~10 times
+    per launch; without `fence.proxy.async` before the barrier whole warps read the next tile's
+    records (seen as 16-64 corrupted rows in ~1/3 of the steps).  60 steps must be bit-identical to
+    the direct kernel."""
+    from gym_ACAS2D.envs import _native
+    lib = _native.load()
+    B = 4 << 20
+    a = make(B, 1, seed=4, auto_reset=True); b = make(B, 1, seed=4, auto_reset=True)
+    a.reset(); b.reset()
+    try:
+        for t in range(60):
+            act = a.random_actions(t, 9)
+            lib.acas2d_set_tuning(occ, -1); lib.acas2d_set_n1_kernel(1, stages)
+            a.step(act, full_outputs=False)
+            lib.acas2d_set_n1_kernel(0, 0)
+            b.step(act, full_outputs=False)
+            assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux), t
+            assert torch.equal(a.obs.view(torch.int32), b.obs.view(torch.int32)) and torch.equal(a.reward, b.reward), t
+    finally:
+        lib.acas2d_set_tuning(4, -1); lib.acas2d_set_n1_kernel(1, 3)
+
+
 def test_sharding_invariance_and_determinism(cuda):
     """1 Mi envs (BASELINE config 3 size): two half-batches addressed by global env id reproduce the
     full batch bit for bit (state, outputs, integer episode counters) -- the multi-GPU property."""
