@@ -95,6 +95,8 @@ inline DevParams make_dev_params(const acas2d_params &p)
     d.inv_rw_goal_max = (float)(1.0 / (d_goal_init + (p.airspeed / p.fps) * p.max_steps));
     d.reward_goal = (float)p.reward_goal;
     d.reward_collision = (float)p.reward_collision;
+    d.tn_x_span_f = (float)d.tn_x_span; d.tn_y_span_f = (float)d.tn_y_span;
+    d.factor_min_f = (float)d.factor_min; d.factor_span_f = (float)d.factor_span; d.airspeed_f = (float)p.airspeed;
     d.n_traffic = p.n_traffic;
     d.max_steps = (int32_t)p.max_steps;
     d.auto_reset = p.auto_reset;
@@ -175,12 +177,12 @@ ACAS_HD bool traffic_store(const StatePtrs &S, int64_t ij, const TrafficRec &t, 
     return need;
 }
 
-ACAS_HD Intruder intruder_at(const DevParams &P, const TrafficRec &t, int k)
+ACAS_HD Intruder intruder_at(const DevParams &P, const TrafficRec &t, double k)
 {
     Intruder it;
     heading_to_velocity(P, t.v, t.psi, &it.dx, &it.dy);
-    it.x = t.x0 + (double)k * it.dx;
-    it.y = t.y0 + (double)k * it.dy;
+    it.x = t.x0 + k * it.dx;
+    it.y = t.y0 + k * it.dy;
     it.vratio = P.uniform_speed ? 1.0 : P.airspeed / t.v;              // Q3
     return it;
 }
@@ -233,7 +235,7 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
     player_advance(P, p);
 
     const int k = e.steps;                                                 // intruder moves after this step
-    Intruder t = intruder_at(P, e.tr, k);                                  // game.py:243-245
+    Intruder t = intruder_at(P, e.tr, (double)k);                          // game.py:243-245
     if (MINSEP) {                                                          // game.py:237 (Q10: old traffic)
         const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
         e.minsep = fminf(e.minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
@@ -297,7 +299,7 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
     p.x = P.player_x0; p.y = P.player_y0;
     player_set_heading(P, p, sp.player_psi, 0.0);                          // a_lat = 0 in a new game
     e.tr = spawn_traffic(P, S.seed, gid, episode, 0, sp);
-    t = intruder_at(P, e.tr, 0);
+    t = intruder_at(P, e.tr, 0.0);
     const PlayerView v1 = player_view(P, p, 1);                            // environment.py:47: steps becomes 1
     const Encounter e1 = encounter(P, p, t);
     if (EMIT) store_obs8(out.obs + 8 * i, v1, e1, P);
@@ -353,8 +355,9 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
     bool coll = false;
     float minsep = MINSEP ? S.min_sep[i] : 0.0f;
     Encounter e0;
+    const double kd = (double)k;
     for (int j = 0; j < N; ++j) {
-        const Intruder t = intruder_at(P, traffic_load(S, i * N + j, residual), k);
+        const Intruder t = intruder_at(P, traffic_load(S, i * N + j, residual), kd);
         if (MINSEP) {
             const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
             minsep = fminf(minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
@@ -409,7 +412,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             for (int j = 0; j < N; ++j) {
                 const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
                 traffic_store(S, i * N + j, tr, false);
-                const Encounter en = encounter(P, p, intruder_at(P, tr, 0));
+                const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
                 minsep = fminf(minsep, en.d);
                 row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
                 row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
@@ -446,7 +449,7 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     for (int j = 0; j < N; ++j) {
         const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
         traffic_store(S, i * N + j, tr, false);
-        const Encounter en = encounter(P, p, intruder_at(P, tr, 0));
+        const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
         minsep = fminf(minsep, en.d);
         if (row) {
             row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
@@ -503,7 +506,7 @@ ACAS_HD void extract_env(const DevParams &P, const StatePtrs &S, int64_t i, doub
         for (int j = 0; j < N; ++j) {
             const int64_t ij = i * N + j;
             const TrafficRec tr = traffic_load(S, ij, (pa.steps & kResidualBit) != 0);
-            const Intruder t = intruder_at(P, tr, st - 1);
+            const Intruder t = intruder_at(P, tr, (double)(st - 1));
             traffic[4 * ij + 0] = t.x;
             traffic[4 * ij + 1] = t.y;
             traffic[4 * ij + 2] = tr.v;

@@ -67,6 +67,7 @@ struct DevParams {
     float inv_rw_dev_max;
     float inv_rw_goal_max;     // 1/3408 at defaults, rewards.py:46-47
     float reward_goal, reward_collision;
+    float tn_x_span_f, tn_y_span_f, factor_min_f, factor_span_f, airspeed_f;   // float32 spawn of intruders n>0
     // ---- integers
     int32_t n_traffic, max_steps, auto_reset, uniform_speed;
 };
@@ -381,18 +382,22 @@ ACAS_HD Spawn0 spawn_slot0(const DevParams &P, uint64_t seed, uint64_t gid, uint
     return o;
 }
 
-// Draw slot i >= 1: intruder i position, speed factor, heading (game.py:109-114).
+// Draw slot i >= 1: intruder i position, speed factor, heading (game.py:109-114).  These values are
+// stored as float32 (acas2d_b200.h "thot"), so they are drawn in float32 to begin with: u = 24 random
+// bits * 2^-24, one float multiply each -- a respawn at large N_TRAFFIC is as hot as a step.
 struct SpawnN { double x, y, v, psi; };
+
+ACAS_HD float u01f(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
 
 ACAS_HD SpawnN spawn_slot(const DevParams &P, uint64_t seed, uint64_t gid, uint32_t episode, uint32_t i)
 {
     const U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), episode, i,
                                (uint32_t)seed, (uint32_t)(seed >> 32));
     SpawnN o;
-    o.x = P.tn_x_span * u01(r.x);
-    o.y = P.tn_y_span * u01(r.y);
-    o.v = (P.factor_min + P.factor_span * u01(r.z)) * P.airspeed;
-    o.psi = 360.0 * u01(r.w);
+    o.x = (double)(P.tn_x_span_f * u01f(r.x));
+    o.y = (double)(P.tn_y_span_f * u01f(r.y));
+    o.v = (double)(fmaf(P.factor_span_f, u01f(r.z), P.factor_min_f) * P.airspeed_f);
+    o.psi = (double)(360.0f * u01f(r.w));
     return o;
 }
 

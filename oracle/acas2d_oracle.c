@@ -446,12 +446,17 @@ static void spawn_one(const acas2d_oracle_params *P, int N, uint64_t seed, uint6
     traffic[3] = acas2d_oracle_pymod(145.0 + (sd * 70.0) + (-tl + (tl - (-tl)) * u01(r[3])), 360.0); /* :105-106 */
 
     for (int i = 1; i < N; ++i) {
+        /* intruders n > 0 are stored as float32, so the new framework draws them in float32:
+         * u = 24 random bits * 2^-24, distributions of game.py:109-114 */
         ctr[3] = (uint32_t)i;
         acas2d_oracle_philox4x32_10(ctr, key, r);
-        traffic[4 * i + 0] = 0.0 + ((P->width - P->aircraft_size) - 0.0) * u01(r[0]); /* game.py:109 */
-        traffic[4 * i + 1] = 0.0 + ((3.0 * P->height / 5.0) - 0.0) * u01(r[1]);        /* :110 */
-        traffic[4 * i + 2] = (fmin + (fmax - fmin) * u01(r[2])) * P->airspeed;         /* :112 */
-        traffic[4 * i + 3] = 0.0 + (360.0 - 0.0) * u01(r[3]);                           /* :114 */
+        const float two24 = 5.9604644775390625e-08f;
+        float u0 = (float)(r[0] >> 8) * two24, u1 = (float)(r[1] >> 8) * two24;
+        float u2 = (float)(r[2] >> 8) * two24, u3 = (float)(r[3] >> 8) * two24;
+        traffic[4 * i + 0] = (double)((float)(P->width - P->aircraft_size) * u0);                  /* game.py:109 */
+        traffic[4 * i + 1] = (double)((float)(3.0 * P->height / 5.0) * u1);                       /* :110 */
+        traffic[4 * i + 2] = (double)(fmaf((float)(fmax - fmin), u2, (float)fmin) * (float)P->airspeed); /* :112 */
+        traffic[4 * i + 3] = (double)(360.0f * u3);                                                /* :114 */
     }
     /* the new framework stores a spawned intruder as four float32 values (DESIGN.md "Data layout") */
     for (int q = 0; q < 4 * N; ++q) traffic[q] = (double)(float)traffic[q];

@@ -212,7 +212,7 @@ def test_tma_ring_kernel_equals_direct_kernel(cuda, stages, occ):
             assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(a.flags, b.flags)
             assert torch.equal(a.term_obs[da], b.term_obs[db]) and torch.equal(a.ep_length[da], b.ep_length[db])
     finally:
-        lib.acas2d_set_tuning(4, -1); lib.acas2d_set_n1_kernel(1, 3)
+        lib.acas2d_set_tuning(3, -1); lib.acas2d_set_n1_kernel(1, 2)
     assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.thot, b.thot)
     assert torch.equal(a.episode_idx, b.episode_idx) and torch.equal(a.episode_counters(), b.episode_counters())
     assert a.episode_counters()[0].item() > 1000
@@ -239,7 +239,7 @@ def test_tma_ring_stress_at_full_size(cuda, stages, occ):
             assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux), t
             assert torch.equal(a.obs.view(torch.int32), b.obs.view(torch.int32)) and torch.equal(a.reward, b.reward), t
     finally:
-        lib.acas2d_set_tuning(4, -1); lib.acas2d_set_n1_kernel(1, 3)
+        lib.acas2d_set_tuning(3, -1); lib.acas2d_set_n1_kernel(1, 2)
 
 
 def test_sharding_invariance_and_determinism(cuda):
