@@ -322,27 +322,34 @@ step_loop_kernel(const DevParams P, const StatePtrs S, const float *__restrict__
 //   6. the observation tile is written back row by row, fully coalesced.
 constexpr int kTiledWarps = 4;
 
-__host__ __device__ inline int tiled_obs_stride(int L, int G) { return (G == 1 && (L & 1)) ? L + 1 : L; }
+// Shared-memory geometry of one warp: traffic tile of E rows x TS float4 (TS = N + 1 for G == 1 so
+// that the 16-byte reads of a quarter warp, one row per lane, fall in distinct banks; TS = N
+// otherwise, where a rotated start does the same job), then E unpadded observation rows.
+__host__ __device__ inline int tiled_row_stride(int N, int G) { return G == 1 ? N + 1 : N; }
 
-inline size_t tiled_smem_bytes(int N, int G)
+inline size_t tiled_warp_bytes(int N, int G)
 {
     const int E = 32 / G, L = 5 + 3 * N;
-    return (size_t)kTiledWarps * ((size_t)E * N * 16 + (((size_t)E * tiled_obs_stride(L, G) * 4 + 15) & ~(size_t)15));
+    return (size_t)E * tiled_row_stride(N, G) * 16 + (((size_t)E * L * 4 + 15) & ~(size_t)15);
 }
+
+inline size_t tiled_smem_bytes(int N, int G) { return kTiledWarps * tiled_warp_bytes(N, G); }
 
 template <int G, bool MINSEP>
 __global__ void __launch_bounds__(kTiledWarps * 32)
-step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out)
+step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
+                  const uint32_t magic_n)
 {
     constexpr int E = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.n_traffic;
     const int L = 5 + 3 * N;
-    const int Lp = tiled_obs_stride(L, G);
+    const int TS = tiled_row_stride(N, G);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t warp_bytes = (size_t)E * N * 16 + (((size_t)E * Lp * 4 + 15) & ~(size_t)15);
+    const size_t tile_bytes = (size_t)E * TS * 16;
+    const size_t warp_bytes = tile_bytes + (((size_t)E * L * 4 + 15) & ~(size_t)15);
     Float4 *tile = (Float4 *)(smem_raw + warp * warp_bytes);
-    float *otile = (float *)(smem_raw + warp * warp_bytes + (size_t)E * N * 16);
+    float *otile = (float *)(smem_raw + warp * warp_bytes + tile_bytes);
 
     const int64_t env0 = ((int64_t)blockIdx.x * kTiledWarps + warp) * E;     // first env of this warp
     Tally tally;
@@ -354,12 +361,15 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         const int64_t env = env0 + (valid ? e : 0);
         const bool lead = valid && sub == 0;
 
-        // 1. stage the traffic tile
+        // 1. stage the traffic tile: contiguous in HBM, 16-byte cp.async, fully coalesced
         {
             const Float4 *src = S.thot + env0 * N;
             const int total = nvalid * N;
-            for (int idx = lane; idx < total; idx += 32)
-                __pipeline_memcpy_async(tile + idx, src + idx, 16);
+            for (int idx = lane; idx < total; idx += 32) {
+                int dst = idx;
+                if (G == 1) dst += (int)__umulhi((unsigned)idx, magic_n);        // + row (row padding)
+                __pipeline_memcpy_async(tile + dst, src + idx, 16);
+            }
             __pipeline_commit();
         }
 
@@ -379,17 +389,19 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         __pipeline_wait_prior(0);
         __syncwarp();
 
-        // 2. intruders of this lane
+        // 2. intruders of this lane: j = sub, sub + G, ... (rotated start for G > 1; G divides N)
         const int per_lane = N / G;
-        int j = lane % N;                              // rotated start; j == sub (mod G) because G | N
+        const int j0 = (G == 1) ? 0 : lane % N;
+        int j = j0;
         bool coll = false;
         Encounter e0;
         e0.d2 = 0.0; e0.d = 0.0f; e0.d_cpa = 0.0f; e0.v_c = 0.0f;
-        float *orow = otile + e * Lp;
+        float *orow = otile + e * L;
+        const Float4 *trow = tile + e * TS;
         const double kd = (double)k;
         const bool any_residual = __any_sync(kFull, residual);      // injected float64 states only: keep it a branch
         for (int m = 0; m < per_lane; ++m) {
-            const Float4 h = tile[e * N + j];
+            const Float4 h = trow[j];
             TrafficRec tr;
             tr.x0 = (double)h.x; tr.y0 = (double)h.y; tr.psi = (double)h.z; tr.v = (double)h.w;
             if (any_residual) {
@@ -410,7 +422,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
             orow[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
             orow[5 + 3 * j + 2] = en.v_c * P.vc_scale;
             j += G;
-            if (j >= N) j -= N;
+            if (G > 1 && j >= N) j -= N;
         }
 
         // 3. reductions over the G lanes of the env
@@ -460,7 +472,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
                 for (int row = 0; row < nvalid; ++row) {
                     if (!((respawn_mask >> (row * G)) & 1u)) continue;          // warp-uniform
                     float *dst = out.term_obs + (env0 + row) * L;
-                    for (int c = lane; c < L; c += 32) dst[c] = otile[row * Lp + c];
+                    for (int c = lane; c < L; c += 32) dst[c] = otile[row * L + c];
                 }
                 __syncwarp();
             }
@@ -473,7 +485,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
                 p.x = P.player_x0; p.y = P.player_y0;
                 player_set_heading(P, p, sp.player_psi, 0.0);
                 minsep = INFINITY;
-                j = lane % N;
+                j = j0;
                 for (int m = 0; m < per_lane; ++m) {
                     const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
                     traffic_store(S, env * N + j, tr, false);
@@ -483,7 +495,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
                     orow[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
                     orow[5 + 3 * j + 2] = en.v_c * P.vc_scale;
                     j += G;
-                    if (j >= N) j -= N;
+                    if (G > 1 && j >= N) j -= N;
                 }
                 if (sub == 0) {
                     const PlayerView v1 = player_view(P, p, 1);
@@ -500,19 +512,17 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         }
         __syncwarp();
 
-        // 6. coalesced write-back of the observation rows (rows of consecutive envs are contiguous in
-        //    HBM; 128-bit stores whenever the warp's span is 16-byte aligned and unpadded)
+        // 6. coalesced write-back: the rows of the warp's consecutive envs are one contiguous span of
+        //    HBM and of the (unpadded) observation tile; 128-bit stores when the span is 16-byte aligned
         const int64_t span0 = env0 * L;
         const int span = nvalid * L;
-        if (Lp == L && ((span0 | span) & 3) == 0) {
+        if (((span0 | span) & 3) == 0) {
             float4 *dst4 = (float4 *)(out.obs + span0);
             const float4 *src4 = (const float4 *)otile;
             for (int c = lane; c < (span >> 2); c += 32) __stcs(dst4 + c, src4[c]);
         } else {
-            for (int row = 0; row < nvalid; ++row) {
-                float *dst = out.obs + (env0 + row) * L;
-                for (int c = lane; c < L; c += 32) __stcs(dst + c, otile[row * Lp + c]);
-            }
+            float *dst = out.obs + span0;
+            for (int c = lane; c < span; c += 32) __stcs(dst + c, otile[c]);
         }
 
         if (lead) {
@@ -540,17 +550,18 @@ int launch_tiled(const DevParams &P, const StatePtrs &S, const float *actions, c
 {
     constexpr int E = 32 / G;
     const size_t smem = tiled_smem_bytes(P.n_traffic, G);
+    const uint32_t magic_n = (uint32_t)((0x100000000ULL + (uint64_t)P.n_traffic - 1) / (uint64_t)P.n_traffic);   // idx / N for idx < 2^16
     const int64_t warps = (S.B + E - 1) / E;
     const unsigned grid = (unsigned)((warps + kTiledWarps - 1) / kTiledWarps);
     cudaError_t err;
     if (S.min_sep) {
         err = cudaFuncSetAttribute(step_tiled_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        step_tiled_kernel<G, true><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out);
+        step_tiled_kernel<G, true><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out, magic_n);
     } else {
         err = cudaFuncSetAttribute(step_tiled_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        step_tiled_kernel<G, false><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out);
+        step_tiled_kernel<G, false><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out, magic_n);
     }
     return 0;
 }
