@@ -54,11 +54,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(n_traffic: int):
-    """DRAM bytes per env-step of the step kernel from the committed ncu capture, if any."""
+def ncu_traffic(n_traffic: int, envs: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json), scaled to this run's envs per launch."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return d.get(f"n{n_traffic}")
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[f"n{n_traffic}"]
+        return d["bytes_per_launch"] * envs / d["envs"]
     except Exception:  # noqa: BLE001
         return None
 
@@ -259,19 +260,25 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident throughput (the `value`): CUDA-graph replay of the step loop, so the
-    #      Python / ctypes launch cost (~100 us per step, as slow as the kernel) is off the clock
+    # ---- device-resident throughput (the `value`): CUDA-graph replay of the step loop (the Python /
+    #      ctypes launch path is timed separately as "eager")
     step_fn = lambda k: env.step(actions[k % KA], full_outputs=False)   # noqa: E731
     for k in range(W):
         step_fn(k)
-    GK = 8 * KA if K >= 8 * KA else KA                  # steps per graph replay
-    replays = max(1, K // GK)
-    K = replays * GK
+    GK = min(K, 8 * KA)                                 # steps per graph replay
+    replays, rest = divmod(K, GK)                       # exactly K steps: `replays` replays + `rest` eager steps
     graph = env.capture_steps(actions, full_outputs=False, num_steps=GK, warmup=False)
     graph.replay()
+
+    def k_steps(_):
+        for _r in range(replays):
+            graph.replay()
+        for k in range(rest):
+            step_fn(k)
+
     with ClockSampler(local) as clocks:
-        ms = timed(lambda k: graph.replay(), replays)
-    launches = replays * GK                              # one step kernel per captured step
+        ms = timed(k_steps, 1)
+    launches = K                                         # one step kernel per env step (graph nodes + eager)
     value = world * B * K / (ms * 1e-3)
     peak, peak_src = measured_peak()
     A = algorithmic_bytes(N)
@@ -321,16 +328,16 @@ def run_ours(args):
                            "l2": "state + outputs per GPU = %.0f MB >> 126 MB L2 (no flush needed)" % (B * (A + 64) / 1e6),
                            "parallelism": f"env-sharded x{world}, one all-reduce of 7 int64 episode counters after the timed region"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": ncu_traffic(N), "peak_source": peak_src,
+                             "traffic": ncu_traffic(N, B), "peak_source": peak_src,
                              "algorithmic_bytes_per_env_step": A, "env_steps_per_launch": B,
                              "note": "per GPU; achieved = A(N) x envs per launch / CUDA-event time per launch"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": (4 * L + 5) * B,
                         "steps": Ke, "ms_per_step": ms_e2e / Ke,
                         "path": "BatchedACAS2D.step_host -> acas2d_step_host (pinned host buffers)"},
                 "gpu_launches": int(launches), "clocks": clocks.summary(),
-                "launch_mode": f"CUDA graph, {GK} step kernels per replay x {replays} replays",
+                "launch_mode": f"CUDA graph, {GK} step kernels per replay x {replays} replays + {rest} eager steps",
                 "eager": {"ms_per_step": ms_eager / max(1, eager_launches), "launches": int(eager_launches),
-                          "note": "same loop launched step by step from Python/ctypes (host launch cost on the clock)"},
+                          "note": "same loop launched step by step from Python/ctypes"},
                 "episode_stats": stats, "other": other}
         if world == 1 and not args.skip_cpu:
             line["cpu_baseline"] = cpu_baseline_block()
