@@ -309,6 +309,19 @@ def run_ours(args):
         ms_f = timed(lambda k: env.rollout_random(fused_k, action_seed=1, step0=100 + fused_k * k), reps)
         other["fused_rollout_64_steps_per_launch"] = {"value": world * B * fused_k * reps / (ms_f * 1e-3), "unit": UNIT,
                                                       "note": "in-kernel Philox actions, state in registers, no per-step outputs"}
+        # closed-loop rollout: the reference's trained actor (8-64-64-1 tanh MLP) fused with the env step
+        from gym_ACAS2D.policy import MlpActor
+        fixture = os.path.join(ROOT, "tests", "golden", "ppo_policy_1048576_11.npz")
+        actor = MlpActor.from_file(fixture, dev) if os.path.exists(fixture) else MlpActor.random(0, dev)
+        pol_steps = 16
+        for k in range(3):
+            env.policy_step(actor, deterministic=False, noise_seed=5, step_index=k, full_outputs=False)
+        ms_p = timed(lambda k: env.policy_step(actor, deterministic=False, noise_seed=5, step_index=10 + k,
+                                               full_outputs=False), pol_steps)
+        other["policy_rollout_fused_mlp_env_step"] = {
+            "value": world * B * pol_steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / pol_steps,
+            "note": "BASELINE config 5 inner loop: SB3 MlpPolicy actor (fp32, CUDA cores) + Gaussian noise + clip + env "
+                    "step in one kernel per step; no host round trip"}
         small = BatchedACAS2D(4096, n_traffic=1, device=dev, seed=13, env_id_offset=0, auto_reset=True)
         small.reset()
         sgraph = small.capture_steps(actions[:, :4096].contiguous(), num_steps=200)      # 200 steps per replay

@@ -26,6 +26,7 @@
 
 #include "../../include/acas2d_b200.h"
 #include "acas2d_env.cuh"
+#include "acas2d_policy.cuh"
 
 namespace {
 
@@ -270,6 +271,44 @@ int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, 
     if (grid > tiles) grid = tiles;
     step_n1_tma_kernel<STAGES, OCC><<<(unsigned)grid, kBlock, STAGES * kStageBytes + 64, st>>>(P, S, actions, out, full_tiles);
     return 0;
+}
+
+// ---------------------------------------------------------------- policy + env step (N_TRAFFIC == 1)
+// Closed-loop rollout step: actor MLP on the env's current observation row, Gaussian exploration noise
+// (optional), clip to the action Box, then the environment step -- one kernel, no host round trip.
+// Persistent blocks: the 19 KB weight block is loaded into shared memory once per block.
+template <bool STOCHASTIC>
+__global__ void __launch_bounds__(kBlock, 2)
+policy_step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ weights,
+                      const float *obs_in, float *__restrict__ actions_out, float *__restrict__ logp_out,
+                      const Sinks out, const float log_std, const uint64_t noise_seed, const uint64_t step_index)
+{
+    __shared__ __align__(16) float sw[kPolFloats];
+    for (int q = threadIdx.x; q < kPolFloats; q += kBlock) sw[q] = weights[q];
+    __syncthreads();
+    Tally tally;
+    tally_clear(tally);
+    const float std_dev = __expf(log_std);
+    for (int64_t base = (int64_t)blockIdx.x * kBlock; base < S.B; base += (int64_t)gridDim.x * kBlock) {
+        const int64_t i = base + threadIdx.x;
+        if (i < S.B) {
+            const float4 o0 = ((const float4 *)obs_in)[2 * i], o1 = ((const float4 *)obs_in)[2 * i + 1];
+            const float obs[kPolObs] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            float a = policy_mean(sw, obs);                                  // model.predict(deterministic=True)
+            if (STOCHASTIC) {
+                const float eps = policy_noise(noise_seed, S.gid0 + (uint64_t)i, step_index);
+                a = fmaf(std_dev, eps, a);
+                if (logp_out) logp_out[i] = -0.5f * eps * eps - log_std - 0.9189385332046727f;   // log N(a; mean, std)
+            }
+            if (actions_out) actions_out[i] = a;                             // rollout buffers keep the unclipped sample
+            const float clipped = fminf(1.0f, fmaxf(-1.0f, a));              // np.clip to the action Box before env.step
+            Env1 e;
+            load_env1(S, i, e, false);
+            step_env1<false, true>(P, S, e, clipped, i, out, tally, nullptr);
+            store_env1(S, i, e, false);
+        }
+    }
+    tally_flush_warp(S.stats, tally);
 }
 
 template <bool MINSEP>
@@ -832,6 +871,37 @@ int acas2d_rollout_random(const acas2d_params *params, const acas2d_state *state
     const unsigned grid = grid_for(state->num_envs);
     if (S.min_sep) rollout_n1_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(P, S, num_steps, action_seed, step0, reward_sum);
     else rollout_n1_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(P, S, num_steps, action_seed, step0, reward_sum);
+    return finish_launch();
+}
+
+int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, const float *weights,
+                       float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
+                       float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
+                       uint64_t noise_seed, uint64_t step_index, void *stream)
+{
+    if (int e = check_args(params, state)) return e;
+    if (params->n_traffic != 1 || state->min_sep) return ACAS2D_E_BAD_TRAFFIC;    // the trained actor takes 8 inputs
+    if (!weights || !obs_in || !obs_out || !reward || !done) return ACAS2D_E_NULL;
+    if (state->num_envs == 0) return 0;
+    const DevParams P = make_dev_params(*params);
+    const StatePtrs S = make_state_ptrs(*state);
+    const Sinks out = make_sinks(obs_out, reward, done, aux);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    long long grid = (long long)sms * 2;
+    const long long tiles = (S.B + kBlock - 1) / kBlock;
+    if (grid > tiles) grid = tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stochastic)
+        policy_step_n1_kernel<true><<<(unsigned)grid, kBlock, 0, st>>>(P, S, weights, obs_in, actions_out, logp_out, out,
+                                                                       log_std, noise_seed, step_index);
+    else
+        policy_step_n1_kernel<false><<<(unsigned)grid, kBlock, 0, st>>>(P, S, weights, obs_in, actions_out, logp_out, out,
+                                                                        log_std, noise_seed, step_index);
     return finish_launch();
 }
 

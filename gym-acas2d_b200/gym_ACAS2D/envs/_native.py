@@ -16,7 +16,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 CSRC_DIR = os.path.join(_PKG_ROOT, "csrc")
 REPO_ROOT = os.path.dirname(_PKG_ROOT)
 LIB_PATH = os.path.join(CSRC_DIR, "libacas2d_b200.so")
-SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh")
+SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -28,10 +28,11 @@ STAT_NAMES = ("episodes", "goal", "collision", "timeout", "length_sum", "return_
 STAT_FX_SCALE = 1048576.0
 FLAG_COLLISION, FLAG_GOAL, FLAG_TIMEOUT, FLAG_DONE, FLAG_OOB = 1, 2, 4, 8, 16
 STEPS_RESIDUAL_BIT = 0x40000000
+POLICY_FLOATS = 4804
 
 EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
-           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel")
+           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -93,6 +94,8 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_launch_count.restype = ctypes.c_int64
     lib.acas2d_set_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.acas2d_set_n1_kernel.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    lib.acas2d_policy_step.argtypes = [PP, SP, vp, ctypes.c_float, vp, vp, vp, vp, vp, vp, AP, ctypes.c_int32,
+                                       ctypes.c_uint64, ctypes.c_uint64, vp]
     return lib
 
 

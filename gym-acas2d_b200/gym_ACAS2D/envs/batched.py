@@ -203,6 +203,28 @@ class BatchedACAS2D:
                 reward_sum.data_ptr() if reward_sum is not None else None, self._stream()), "acas2d_rollout_random")
         self.launches += 1
 
+    def policy_step(self, actor, deterministic: bool = True, noise_seed: int = 0, step_index: int = 0,
+                    actions_out: Optional[torch.Tensor] = None, logp_out: Optional[torch.Tensor] = None,
+                    obs_in: Optional[torch.Tensor] = None, full_outputs: bool = True):
+        """Closed-loop step: ``actor`` (``gym_ACAS2D.policy.MlpActor`` on this device) is evaluated on the
+        current observation rows (default: this object's ``obs`` buffer, i.e. the previous step's output),
+        its action -- ``model.predict(obs, deterministic=...)`` semantics, clipped to the Box -- is applied,
+        all in one kernel.  Returns the (obs, reward, done) buffers; the unclipped action sample and its
+        log-probability go to ``actions_out`` / ``logp_out`` when given."""
+        if actor.packed.device != self.device:
+            actor.to(self.device)
+        src = self.obs if obs_in is None else obs_in
+        aux = self._aux_full if full_outputs else self._aux_lean
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_policy_step(
+                self._p(), self._s(), actor.packed.data_ptr(), float(actor.log_std), src.data_ptr(),
+                actions_out.data_ptr() if actions_out is not None else None,
+                logp_out.data_ptr() if logp_out is not None else None,
+                self.obs.data_ptr(), self.reward.data_ptr(), self.done_u8.data_ptr(), ctypes.byref(aux),
+                0 if deterministic else 1, int(noise_seed), int(step_index), self._stream()), "acas2d_policy_step")
+        self.launches += 1
+        return self.obs, self.reward, self.done
+
     def capture_steps(self, actions: torch.Tensor, full_outputs: bool = False, num_steps: Optional[int] = None,
                       warmup: bool = True) -> "torch.cuda.CUDAGraph":
         """Capture consecutive steps into one CUDA graph (replay with ``graph.replay()``): step k uses

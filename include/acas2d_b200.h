@@ -188,6 +188,22 @@ int acas2d_rollout_random(const acas2d_params *params, const acas2d_state *state
 int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed,
                           uint64_t step_index, float *actions, void *stream);
 
+/* Closed-loop rollout step for the reference's trained agent (N_TRAFFIC == 1): evaluates the SB3
+ * MlpPolicy actor saved by gym_ACAS2D/training_main.py:44-52 (policy.pth: mlp_extractor.policy_net
+ * 8 -> 64 -> 64 tanh, action_net 64 -> 1) on obs_in float[B][8], optionally adds N(0, exp(log_std)^2)
+ * exploration noise from Philox(key = noise_seed, counter = (global env id, step_index)), clips to the
+ * action Box and performs acas2d_step with that action -- one kernel.  This is what
+ * `model.predict(obs, deterministic=True)` + `env.step` (testing_main.py:74-78) or SB3's rollout
+ * collection does per step.  weights: float[ACAS2D_POLICY_FLOATS] device block packed as
+ * W1[64][8] | b1[64] | W2[64][64] | b2[64] | W3[64] | b3[1] | 3 pad (rows as SB3 stores them).
+ * actions_out float[B] (the unclipped sample; may be NULL), logp_out float[B] (log-probability of
+ * the sample; stochastic only; may be NULL).  obs_in and obs_out may be the same buffer. */
+#define ACAS2D_POLICY_FLOATS 4804
+int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, const float *weights,
+                       float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
+                       float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
+                       uint64_t noise_seed, uint64_t step_index, void *stream);
+
 /* Kernels launched by this library since load (all entry points). */
 int64_t acas2d_launch_count(void);
 

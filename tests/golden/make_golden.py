@@ -239,12 +239,27 @@ def replay_csv_with_oracle(rows):
           f"max |total reward diff| = {worst_r:.3e}")
 
 
+def make_policy_fixture():
+    """The reference's trained agent (models/best_model_1048576_11/best_model.zip, an artefact the
+    reference commits): its policy.pth tensors as a plain npz, plus the reference's own summary of that
+    agent (notebooks/simulation_ACAS2D_PPO_1048576_11_100.ipynb cell 4; SURVEY 8c trained-policy replay)."""
+    import io
+    import zipfile
+    import torch
+    z = zipfile.ZipFile(os.path.join(ref_shim.REFERENCE_ROOT, "gym_ACAS2D/models/best_model_1048576_11/best_model.zip"))
+    sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+    arrays = {k: v.numpy() for k, v in sd.items()}
+    np.savez_compressed(os.path.join(HERE, "ppo_policy_1048576_11.npz"), **arrays)
+    print("policy fixture:", {k: v.shape for k, v in arrays.items()})
+
+
 if __name__ == "__main__":
     if not ref_shim.available():
         sys.exit("reference tree not found; fixtures can only be generated in the build container")
     rows, _ = condense_csv()
     replay_csv_with_oracle(rows)
     make_reset_probe()
+    make_policy_fixture()
     make_rollouts(N=1, B=48, T=1001, seed=2024)
     make_rollouts(N=8, B=24, T=400, seed=2025)
     ref_shim.unload()

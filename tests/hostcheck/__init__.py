@@ -21,7 +21,7 @@ _LIB = os.path.join(_HERE, "libacas2d_hostcheck.so")
 
 
 def build() -> str:
-    srcs = [os.path.join(_HERE, "hostcheck.cpp")] + [os.path.join(_native.CSRC_DIR, s) for s in ("acas2d_env.cuh", "acas2d_math.cuh")]
+    srcs = [os.path.join(_HERE, "hostcheck.cpp")] + [os.path.join(_native.CSRC_DIR, s) for s in ("acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh")]
     if not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", _LIB,
                         os.path.join(_HERE, "hostcheck.cpp"), "-lm"], check=True)

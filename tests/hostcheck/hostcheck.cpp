@@ -7,6 +7,7 @@
 #include <cmath>
 
 #include "../../gym-acas2d_b200/csrc/acas2d_env.cuh"
+#include "../../gym-acas2d_b200/csrc/acas2d_policy.cuh"
 
 using namespace acas2d;
 
@@ -134,5 +135,15 @@ void hostcheck_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
 }
 
 double hostcheck_wrap360(double t) { return wrap360(t); }
+
+void hostcheck_policy_mean(const float *weights, const float *obs, int64_t B, float *mean)
+{
+    for (int64_t i = 0; i < B; ++i) mean[i] = policy_mean(weights, obs + 8 * i);
+}
+
+void hostcheck_policy_noise(uint64_t seed, uint64_t gid0, uint64_t step, int64_t B, float *eps)
+{
+    for (int64_t i = 0; i < B; ++i) eps[i] = policy_noise(seed, gid0 + (uint64_t)i, step);
+}
 
 }  // extern "C"
