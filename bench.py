@@ -322,6 +322,13 @@ def run_ours(args):
             "value": world * B * pol_steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / pol_steps,
             "note": "BASELINE config 5 inner loop: SB3 MlpPolicy actor (fp32, CUDA cores) + Gaussian noise + clip + env "
                     "step in one kernel per step; no host round trip"}
+        for k in range(3):
+            env.policy_step(actor, deterministic=False, noise_seed=5, step_index=k, full_outputs=False, tensor_cores=True)
+        ms_t = timed(lambda k: env.policy_step(actor, deterministic=False, noise_seed=5, step_index=40 + k,
+                                               full_outputs=False, tensor_cores=True), 4 * pol_steps)
+        other["policy_rollout_tcgen05_mlp_env_step"] = {
+            "value": world * B * 4 * pol_steps / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / (4 * pol_steps),
+            "note": "same, hidden layers as tcgen05.mma kind::tf32 with TMEM accumulators (128 envs per CTA tile)"}
         small = BatchedACAS2D(4096, n_traffic=1, device=dev, seed=13, env_id_offset=0, auto_reset=True)
         small.reset()
         sgraph = small.capture_steps(actions[:, :4096].contiguous(), num_steps=200)      # 200 steps per replay

@@ -26,7 +26,8 @@
 
 #include "../../include/acas2d_b200.h"
 #include "acas2d_env.cuh"
-#include "acas2d_policy.cuh"
+#include "acas2d_dev.cuh"
+#include "acas2d_policy_tc.cuh"
 
 namespace {
 
@@ -35,7 +36,6 @@ using namespace acas2d;
 std::atomic<int64_t> g_launches{0};
 
 constexpr int kBlock = 256;
-constexpr unsigned kFull = 0xffffffffu;
 
 int check_args(const acas2d_params *p, const acas2d_state *s)
 {
@@ -73,41 +73,6 @@ Tuning &tuning()
     return t;
 }
 
-// ---------------------------------------------------------------- warp-level statistics flush
-__device__ __forceinline__ long long warp_sum_ll(long long v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
-
-// All 32 lanes must call.  One set of atomics per warp that saw a finished episode, spread
-// over ACAS2D_STAT_SLOTS 128-byte slots so that same-address serialisation stays negligible.
-__device__ __forceinline__ void tally_flush_warp(long long *stats, const Tally &t)
-{
-    if (stats == nullptr) return;
-    if (!__any_sync(kFull, t.episodes != 0)) return;
-    const int episodes = __reduce_add_sync(kFull, t.episodes);
-    const int goal = __reduce_add_sync(kFull, t.goal);
-    const int coll = __reduce_add_sync(kFull, t.coll);
-    const int tout = __reduce_add_sync(kFull, t.tout);
-    const long long length = warp_sum_ll(t.length);
-    const long long ret_fx = warp_sum_ll(t.ret_fx);
-    const long long minsep_fx = warp_sum_ll(t.minsep_fx);
-    if ((threadIdx.x & 31) == 0) {
-        const unsigned warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        unsigned long long *slot = (unsigned long long *)stats +
-                                   (size_t)(warp_global % ACAS2D_STAT_SLOTS) * ACAS2D_STAT_FIELDS;
-        atomicAdd(slot + ACAS2D_STAT_EPISODES, (unsigned long long)episodes);
-        if (goal) atomicAdd(slot + ACAS2D_STAT_GOAL, (unsigned long long)goal);
-        if (coll) atomicAdd(slot + ACAS2D_STAT_COLLISION, (unsigned long long)coll);
-        if (tout) atomicAdd(slot + ACAS2D_STAT_TIMEOUT, (unsigned long long)tout);
-        atomicAdd(slot + ACAS2D_STAT_LENGTH, (unsigned long long)length);
-        atomicAdd(slot + ACAS2D_STAT_RETURN_FX, (unsigned long long)ret_fx);
-        if (minsep_fx) atomicAdd(slot + ACAS2D_STAT_MINSEP_FX, (unsigned long long)minsep_fx);
-    }
-}
-
 template <bool MINSEP, int OCC>
 __global__ void __launch_bounds__(kBlock, OCC)
 step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out)
@@ -138,36 +103,6 @@ step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ a
 constexpr int kTileEnvs = kBlock;
 constexpr int kStageBytes = kTileEnvs * (16 + 16 + 16 + 4);          // ppos | paux | thot | action
 constexpr int kOffPaux = kTileEnvs * 16, kOffThot = kTileEnvs * 32, kOffAct = kTileEnvs * 48;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t addr, unsigned parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gmem_src, unsigned bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
-}
 
 template <int STAGES, int OCC>
 __global__ void __launch_bounds__(kBlock, OCC)
@@ -877,7 +812,7 @@ int acas2d_rollout_random(const acas2d_params *params, const acas2d_state *state
 int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, const float *weights,
                        float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
                        float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
-                       uint64_t noise_seed, uint64_t step_index, void *stream)
+                       uint64_t noise_seed, uint64_t step_index, int32_t tensor_cores, void *stream)
 {
     if (int e = check_args(params, state)) return e;
     if (params->n_traffic != 1 || state->min_sep) return ACAS2D_E_BAD_TRAFFIC;    // the trained actor takes 8 inputs
@@ -892,10 +827,28 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tensor_cores) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(policy_step_n1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+            cudaFuncSetAttribute(policy_step_n1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+            attr_set = true;
+        }
+        long long g = (long long)sms * 3;                   // 3 CTAs/SM: 56 KB smem + 128 TMEM columns each
+        const long long t = (S.B + kTcTile - 1) / kTcTile;
+        if (g > t) g = t;
+        if (stochastic)
+            policy_step_n1_tc_kernel<true><<<(unsigned)g, kTcTile, kTcSmemBytes, st>>>(
+                P, S, weights, obs_in, actions_out, logp_out, out, log_std, noise_seed, step_index);
+        else
+            policy_step_n1_tc_kernel<false><<<(unsigned)g, kTcTile, kTcSmemBytes, st>>>(
+                P, S, weights, obs_in, actions_out, logp_out, out, log_std, noise_seed, step_index);
+        return finish_launch();
+    }
     long long grid = (long long)sms * 2;
     const long long tiles = (S.B + kBlock - 1) / kBlock;
     if (grid > tiles) grid = tiles;
-    cudaStream_t st = (cudaStream_t)stream;
     if (stochastic)
         policy_step_n1_kernel<true><<<(unsigned)grid, kBlock, 0, st>>>(P, S, weights, obs_in, actions_out, logp_out, out,
                                                                        log_std, noise_seed, step_index);

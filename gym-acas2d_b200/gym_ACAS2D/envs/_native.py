@@ -16,7 +16,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 CSRC_DIR = os.path.join(_PKG_ROOT, "csrc")
 REPO_ROOT = os.path.dirname(_PKG_ROOT)
 LIB_PATH = os.path.join(CSRC_DIR, "libacas2d_b200.so")
-SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh")
+SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh", "acas2d_policy_tc.cuh", "acas2d_dev.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -95,7 +95,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_set_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.acas2d_set_n1_kernel.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.acas2d_policy_step.argtypes = [PP, SP, vp, ctypes.c_float, vp, vp, vp, vp, vp, vp, AP, ctypes.c_int32,
-                                       ctypes.c_uint64, ctypes.c_uint64, vp]
+                                       ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, vp]
     return lib
 
 

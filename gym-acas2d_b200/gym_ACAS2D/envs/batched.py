@@ -205,12 +205,13 @@ class BatchedACAS2D:
 
     def policy_step(self, actor, deterministic: bool = True, noise_seed: int = 0, step_index: int = 0,
                     actions_out: Optional[torch.Tensor] = None, logp_out: Optional[torch.Tensor] = None,
-                    obs_in: Optional[torch.Tensor] = None, full_outputs: bool = True):
+                    obs_in: Optional[torch.Tensor] = None, full_outputs: bool = True, tensor_cores: bool = False):
         """Closed-loop step: ``actor`` (``gym_ACAS2D.policy.MlpActor`` on this device) is evaluated on the
         current observation rows (default: this object's ``obs`` buffer, i.e. the previous step's output),
         its action -- ``model.predict(obs, deterministic=...)`` semantics, clipped to the Box -- is applied,
         all in one kernel.  Returns the (obs, reward, done) buffers; the unclipped action sample and its
-        log-probability go to ``actions_out`` / ``logp_out`` when given."""
+        log-probability go to ``actions_out`` / ``logp_out`` when given.  ``tensor_cores`` runs the two
+        hidden layers as tcgen05 TF32 MMAs (TMEM accumulators) instead of float32 on the CUDA cores."""
         if actor.packed.device != self.device:
             actor.to(self.device)
         src = self.obs if obs_in is None else obs_in
@@ -221,7 +222,8 @@ class BatchedACAS2D:
                 actions_out.data_ptr() if actions_out is not None else None,
                 logp_out.data_ptr() if logp_out is not None else None,
                 self.obs.data_ptr(), self.reward.data_ptr(), self.done_u8.data_ptr(), ctypes.byref(aux),
-                0 if deterministic else 1, int(noise_seed), int(step_index), self._stream()), "acas2d_policy_step")
+                0 if deterministic else 1, int(noise_seed), int(step_index), 1 if tensor_cores else 0,
+                self._stream()), "acas2d_policy_step")
         self.launches += 1
         return self.obs, self.reward, self.done
 

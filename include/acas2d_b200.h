@@ -197,12 +197,14 @@ int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed,
  * collection does per step.  weights: float[ACAS2D_POLICY_FLOATS] device block packed as
  * W1[64][8] | b1[64] | W2[64][64] | b2[64] | W3[64] | b3[1] | 3 pad (rows as SB3 stores them).
  * actions_out float[B] (the unclipped sample; may be NULL), logp_out float[B] (log-probability of
- * the sample; stochastic only; may be NULL).  obs_in and obs_out may be the same buffer. */
+ * the sample; stochastic only; may be NULL).  obs_in and obs_out may be the same buffer.
+ * tensor_cores: 0 = float32 on the CUDA cores (matches a torch float32 forward to ~1e-6);
+ * 1 = both hidden layers as tcgen05.mma kind::tf32 with TMEM accumulators (action mean within ~2e-3). */
 #define ACAS2D_POLICY_FLOATS 4804
 int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, const float *weights,
                        float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
                        float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
-                       uint64_t noise_seed, uint64_t step_index, void *stream);
+                       uint64_t noise_seed, uint64_t step_index, int32_t tensor_cores, void *stream);
 
 /* Kernels launched by this library since load (all entry points). */
 int64_t acas2d_launch_count(void);

@@ -90,7 +90,33 @@ def test_fused_policy_step_matches_torch_policy_plus_env_step():
 
 
 @pytest.mark.gpu
-def test_trained_policy_statistics_on_gpu():
+def test_tensor_core_policy_step_matches_fp32_reference():
+    """tcgen05 TF32 path (TMEM accumulators, tanh.approx): action mean within 3e-3 of the torch float32
+    forward pass (stated tolerance: TF32 keeps 10 mantissa bits), and the env-step half of the fused
+    kernel is bit-identical to the plain step fed with the kernel's own actions.  Ragged batch."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import BatchedACAS2D
+    actor = MlpActor.from_file(FIXTURE, "cuda:0")
+    B = 128 * 148 * 3 * 2 + 128 * 5 + 41
+    a = BatchedACAS2D(B, seed=6, auto_reset=True); b = BatchedACAS2D(B, seed=6, auto_reset=True)
+    oa = a.reset(); b.reset()
+    acts = torch.zeros(B, device="cuda")
+    worst = 0.0
+    for t in range(200):
+        ref_mean = actor.reference_mean(oa)
+        oa, ra, da = a.policy_step(actor, deterministic=True, actions_out=acts, tensor_cores=True)
+        worst = max(worst, float((acts - ref_mean).abs().max()))
+        ob, rb, db = b.step(acts.clamp(-1, 1))
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+    assert worst < 3e-3, worst
+    assert torch.equal(a.ppos, b.ppos) and torch.equal(a.episode_counters(), b.episode_counters())
+    print(f"tcgen05 policy: max |action mean - fp32 reference| = {worst:.2e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_trained_policy_statistics_on_gpu(tensor_cores):
     """Same external pin as the oracle test, through the fused kernel: 8192 first episodes."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
@@ -103,7 +129,7 @@ def test_trained_policy_statistics_on_gpu():
     outcome = torch.zeros(B, dtype=torch.uint8, device="cuda"); length = torch.zeros(B, dtype=torch.int32, device="cuda")
     ret = torch.zeros(B, device="cuda")
     for _ in range(1001):
-        _, _, d = env.policy_step(actor, deterministic=True)
+        _, _, d = env.policy_step(actor, deterministic=True, tensor_cores=tensor_cores)
         new = d & ~finished
         outcome[new] = env.outcome[new]; length[new] = env.ep_length[new]; ret[new] = env.ep_return[new]
         finished |= new
@@ -112,4 +138,4 @@ def test_trained_policy_statistics_on_gpu():
     assert goal_rate >= 0.97, goal_rate
     assert abs(float(length.float().mean()) - 705) < 10
     assert abs(float(ret.mean()) - 1209) < 20
-    print(f"trained policy on GPU env: goal {goal_rate:.4f}, mean steps {float(length.float().mean()):.1f}, mean return {float(ret.mean()):.1f}")
+    print(f"trained policy on GPU env (tensor_cores={tensor_cores}): goal {goal_rate:.4f}, mean steps {float(length.float().mean()):.1f}, mean return {float(ret.mean()):.1f}")
