@@ -835,7 +835,7 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
             cudaFuncSetAttribute(policy_step_n1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
             attr_set = true;
         }
-        long long g = (long long)sms * 3;                   // 3 CTAs/SM: 56 KB smem + 128 TMEM columns each
+        long long g = (long long)sms * 4;                   // 4 CTAs/SM: 52 KB smem + 64 TMEM columns each
         const long long t = (S.B + kTcTile - 1) / kTcTile;
         if (g > t) g = t;
         if (stochastic)

@@ -22,14 +22,15 @@
 namespace acas2d {
 
 constexpr int kTcTile = 128;                        // envs per tile == threads per CTA
-constexpr int kTcA1 = 0;                            // OBS  : 128 rows x 8  tf32 = 2 chunks x 2048 B
-constexpr int kTcB1 = kTcA1 + 2 * 2048;             // W1   :  64 rows x 8  tf32 = 2 chunks x 1024 B
-constexpr int kTcA2 = kTcB1 + 2 * 1024;             // H1   : 128 rows x 64 tf32 = 16 chunks x 2048 B
-constexpr int kTcB2 = kTcA2 + 16 * 2048;            // W2   :  64 rows x 64 tf32 = 16 chunks x 1024 B
+constexpr int kTcA2 = 0;                            // H1   : 128 rows x 64 tf32 = 16 chunks x 2048 B
+constexpr int kTcA1 = kTcA2;                        // OBS  : 128 rows x 8  tf32 = 2 chunks x 2048 B; aliases H1's
+                                                    //        first two chunks (dead once layer 1 has completed)
+constexpr int kTcB1 = kTcA2 + 16 * 2048;            // W1   :  64 rows x 8  tf32 = 2 chunks x 1024 B
+constexpr int kTcB2 = kTcB1 + 2 * 1024;             // W2   :  64 rows x 64 tf32 = 16 chunks x 1024 B
 constexpr int kTcVec = kTcB2 + 16 * 1024;           // b1[64] | b2[64] | w3[64] | b3
 constexpr int kTcBar = kTcVec + 200 * 4;            // mbarrier (8 B) + TMEM base address (4 B)
 constexpr int kTcSmemBytes = kTcBar + 16;
-constexpr uint32_t kTcTmemCols = 128;
+constexpr uint32_t kTcTmemCols = 64;                // D1 and D2 share the columns: D1 is drained before layer 2 is issued
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading /
 // stride byte offsets in 16-byte units, version 1 (Blackwell), SWIZZLE_NONE.
@@ -82,7 +83,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
 }
 
 template <bool STOCHASTIC>
-__global__ void __launch_bounds__(kTcTile, 3)
+__global__ void __launch_bounds__(kTcTile, 4)
 policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ weights,
                          const float *obs_in, float *__restrict__ actions_out, float *__restrict__ logp_out,
                          const Sinks out, const float log_std, const uint64_t noise_seed, const uint64_t step_index)
@@ -133,15 +134,29 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
     Tally tally;
     tally_clear(tally);
 
+    // Software prefetch: the records of the NEXT tile are requested before this tile's MMAs and
+    // epilogues, so the two global-load latencies of a tile are off its critical path.
+    struct Rec { float4 o0, o1; Vec2d pp; PlayerAux pa; Float4 h; };
+    auto fetch = [&](int64_t i, Rec &r) {
+        if (i < S.B) {
+            r.o0 = ((const float4 *)obs_in)[2 * i]; r.o1 = ((const float4 *)obs_in)[2 * i + 1];
+            r.pp = S.ppos[i]; r.pa = S.paux[i]; r.h = S.thot[i];
+        } else {
+            r.o0 = make_float4(0.f, 0.f, 0.f, 0.f); r.o1 = r.o0;
+        }
+    };
+    Rec nxt;
+    fetch((int64_t)blockIdx.x * kTcTile + tid, nxt);
+
     for (int64_t base = (int64_t)blockIdx.x * kTcTile; base < S.B; base += (int64_t)gridDim.x * kTcTile) {
         const int64_t i = base + tid;
         const bool valid = i < S.B;
+        const Rec cur = nxt;
+        fetch(i + (int64_t)gridDim.x * kTcTile, nxt);
 
         // ---- A1 <- this env's observation row (two 16-byte chunks)
-        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-        if (valid) { o0 = ((const float4 *)obs_in)[2 * i]; o1 = ((const float4 *)obs_in)[2 * i + 1]; }
-        *(float4 *)(smem + kTcA1 + tid * 16) = o0;
-        *(float4 *)(smem + kTcA1 + 2048 + tid * 16) = o1;
+        *(float4 *)(smem + kTcA1 + tid * 16) = cur.o0;
+        *(float4 *)(smem + kTcA1 + 2048 + tid * 16) = cur.o1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");          // also orders last tile's tcgen05.ld
         __syncthreads();
@@ -181,7 +196,7 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                umma_tf32(tmem_base + 64, umma_desc(smem_base + kTcA2 + k * 2 * 2048, 2048, 128),
+                umma_tf32(tmem_base, umma_desc(smem_base + kTcA2 + k * 2 * 2048, 2048, 128),
                           umma_desc(smem_base + kTcB2 + k * 2 * 1024, 1024, 128), idesc, k > 0 ? 1u : 0u);
             umma_commit(bar_addr);
         }
@@ -194,7 +209,7 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
-            tmem_ld32(tmem_lane + 64 + half * 32, v);
+            tmem_ld32(tmem_lane + half * 32, v);
 #pragma unroll
             for (int q = 0; q < 32; ++q)
                 mean = fmaf(sVec[128 + half * 32 + q], tanh_mufu(v[q] + sVec[64 + half * 32 + q]), mean);
@@ -209,7 +224,16 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             if (actions_out) actions_out[i] = a;
             const float clipped = fminf(1.0f, fmaxf(-1.0f, a));
             Env1 e;
-            load_env1(S, i, e, false);
+            e.px = cur.pp.x; e.py = cur.pp.y; e.psi = cur.pa.psi; e.ret = cur.pa.ep_return;
+            e.steps = cur.pa.steps & kStepsMask;
+            e.residual = (cur.pa.steps & kResidualBit) != 0;
+            e.tr.x0 = (double)cur.h.x; e.tr.y0 = (double)cur.h.y; e.tr.psi = (double)cur.h.z; e.tr.v = (double)cur.h.w;
+            if (__builtin_expect(e.residual, 0)) {
+                const Residual r = S.tres[i];
+                e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
+            }
+            e.minsep = 0.0f;
+            e.respawned = false;
             step_env1<false, true>(P, S, e, clipped, i, out, tally, nullptr);
             store_env1(S, i, e, false);
         }
