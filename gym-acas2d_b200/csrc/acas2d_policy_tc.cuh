@@ -178,12 +178,12 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             tmem_ld32(tmem_lane + half * 32, v);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const int j = half * 32 + c * 4;
+                const float4 b = *(const float4 *)(sVec + half * 32 + c * 4);       // b1, broadcast 16-byte read
                 float4 h;
-                h.x = tanh_mufu(v[c * 4 + 0] + sVec[j + 0]);
-                h.y = tanh_mufu(v[c * 4 + 1] + sVec[j + 1]);
-                h.z = tanh_mufu(v[c * 4 + 2] + sVec[j + 2]);
-                h.w = tanh_mufu(v[c * 4 + 3] + sVec[j + 3]);
+                h.x = tanh_mufu(v[c * 4 + 0] + b.x);
+                h.y = tanh_mufu(v[c * 4 + 1] + b.y);
+                h.z = tanh_mufu(v[c * 4 + 2] + b.z);
+                h.w = tanh_mufu(v[c * 4 + 3] + b.w);
                 *(float4 *)(smem + kTcA2 + (half * 8 + c) * 2048 + tid * 16) = h;
             }
         }
@@ -211,8 +211,14 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             float v[32];
             tmem_ld32(tmem_lane + half * 32, v);
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-                mean = fmaf(sVec[128 + half * 32 + q], tanh_mufu(v[q] + sVec[64 + half * 32 + q]), mean);
+            for (int c = 0; c < 8; ++c) {
+                const float4 b = *(const float4 *)(sVec + 64 + half * 32 + c * 4);   // b2
+                const float4 w = *(const float4 *)(sVec + 128 + half * 32 + c * 4);  // w3
+                mean = fmaf(w.x, tanh_mufu(v[c * 4 + 0] + b.x), mean);
+                mean = fmaf(w.y, tanh_mufu(v[c * 4 + 1] + b.y), mean);
+                mean = fmaf(w.z, tanh_mufu(v[c * 4 + 2] + b.z), mean);
+                mean = fmaf(w.w, tanh_mufu(v[c * 4 + 3] + b.w), mean);
+            }
         }
         if (valid) {
             float a = mean;

@@ -205,27 +205,58 @@ class BatchedACAS2D:
 
     def policy_step(self, actor, deterministic: bool = True, noise_seed: int = 0, step_index: int = 0,
                     actions_out: Optional[torch.Tensor] = None, logp_out: Optional[torch.Tensor] = None,
-                    obs_in: Optional[torch.Tensor] = None, full_outputs: bool = True, tensor_cores: bool = False):
+                    obs_in: Optional[torch.Tensor] = None, full_outputs: bool = True, tensor_cores: bool = False,
+                    obs_out: Optional[torch.Tensor] = None, reward_out: Optional[torch.Tensor] = None,
+                    done_out: Optional[torch.Tensor] = None):
         """Closed-loop step: ``actor`` (``gym_ACAS2D.policy.MlpActor`` on this device) is evaluated on the
         current observation rows (default: this object's ``obs`` buffer, i.e. the previous step's output),
         its action -- ``model.predict(obs, deterministic=...)`` semantics, clipped to the Box -- is applied,
         all in one kernel.  Returns the (obs, reward, done) buffers; the unclipped action sample and its
         log-probability go to ``actions_out`` / ``logp_out`` when given.  ``tensor_cores`` runs the two
-        hidden layers as tcgen05 TF32 MMAs (TMEM accumulators) instead of float32 on the CUDA cores."""
+        hidden layers as tcgen05 TF32 MMAs (TMEM accumulators) instead of float32 on the CUDA cores.
+        ``obs_out`` / ``reward_out`` / ``done_out`` (uint8) redirect the step's outputs, e.g. into row t+1 /
+        row t of rollout buffers, so collecting a rollout copies nothing."""
         if actor.packed.device != self.device:
             actor.to(self.device)
         src = self.obs if obs_in is None else obs_in
+        o_dst = self.obs if obs_out is None else obs_out
+        r_dst = self.reward if reward_out is None else reward_out
+        d_dst = self.done_u8 if done_out is None else done_out
         aux = self._aux_full if full_outputs else self._aux_lean
         with torch.cuda.device(self.device):
             _native.check(self.lib.acas2d_policy_step(
                 self._p(), self._s(), actor.packed.data_ptr(), float(actor.log_std), src.data_ptr(),
                 actions_out.data_ptr() if actions_out is not None else None,
                 logp_out.data_ptr() if logp_out is not None else None,
-                self.obs.data_ptr(), self.reward.data_ptr(), self.done_u8.data_ptr(), ctypes.byref(aux),
+                o_dst.data_ptr(), r_dst.data_ptr(), d_dst.data_ptr(), ctypes.byref(aux),
                 0 if deterministic else 1, int(noise_seed), int(step_index), 1 if tensor_cores else 0,
                 self._stream()), "acas2d_policy_step")
         self.launches += 1
-        return self.obs, self.reward, self.done
+        return o_dst, r_dst, d_dst.view(torch.bool)
+
+    def collect_rollout(self, actor, n_steps: int, noise_seed: int = 0, step0: int = 0, tensor_cores: bool = True,
+                        buffers: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """PPO-style rollout collection (what SB3's ``collect_rollouts`` does for the reference's
+        ``PPO(...).learn``, training_main.py:44-52): ``n_steps`` stochastic closed-loop steps from the
+        current observations, written straight into [T, B] buffers -- ``obs`` [T+1, B, L] (row t is what
+        the actor saw at step t; row T bootstraps the value), ``actions``, ``logp``, ``rewards`` [T, B]
+        float32, ``dones`` [T, B] uint8.  One fused kernel per step, no copies, no host round trip."""
+        T, B, L, dev = int(n_steps), self.num_envs, self.obs_dim, self.device
+        if buffers is None:
+            buffers = dict(obs=torch.empty(T + 1, B, L, dtype=torch.float32, device=dev),
+                           actions=torch.empty(T, B, dtype=torch.float32, device=dev),
+                           logp=torch.empty(T, B, dtype=torch.float32, device=dev),
+                           rewards=torch.empty(T, B, dtype=torch.float32, device=dev),
+                           dones=torch.empty(T, B, dtype=torch.uint8, device=dev))
+        buffers["obs"][0].copy_(self.obs)
+        for t in range(T):
+            self.policy_step(actor, deterministic=False, noise_seed=noise_seed, step_index=step0 + t,
+                             actions_out=buffers["actions"][t], logp_out=buffers["logp"][t],
+                             obs_in=buffers["obs"][t], obs_out=buffers["obs"][t + 1],
+                             reward_out=buffers["rewards"][t], done_out=buffers["dones"][t],
+                             full_outputs=False, tensor_cores=tensor_cores)
+        self.obs.copy_(buffers["obs"][T])
+        return buffers
 
     def capture_steps(self, actions: torch.Tensor, full_outputs: bool = False, num_steps: Optional[int] = None,
                       warmup: bool = True) -> "torch.cuda.CUDAGraph":

@@ -139,3 +139,26 @@ def test_trained_policy_statistics_on_gpu(tensor_cores):
     assert abs(float(length.float().mean()) - 705) < 10
     assert abs(float(ret.mean()) - 1209) < 20
     print(f"trained policy on GPU env (tensor_cores={tensor_cores}): goal {goal_rate:.4f}, mean steps {float(length.float().mean()):.1f}, mean return {float(ret.mean()):.1f}")
+
+
+@pytest.mark.gpu
+def test_collect_rollout_buffers_are_consistent():
+    """PPO-style collection: [T, B] buffers written in place by the fused kernel equal a step-by-step
+    rollout with the same noise stream, and obs[t+1] is what step t produced."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import BatchedACAS2D
+    actor = MlpActor.from_file(FIXTURE, "cuda:0")
+    B, T = 3000, 48
+    a = BatchedACAS2D(B, seed=8, auto_reset=True); b = BatchedACAS2D(B, seed=8, auto_reset=True)
+    a.reset(); b.reset()
+    buf = a.collect_rollout(actor, T, noise_seed=21, step0=100, tensor_cores=False)
+    acts = torch.zeros(B, device="cuda"); logp = torch.zeros(B, device="cuda")
+    for t in range(T):
+        assert torch.equal(buf["obs"][t], b.obs)
+        o, r, d = b.policy_step(actor, deterministic=False, noise_seed=21, step_index=100 + t, actions_out=acts, logp_out=logp)
+        assert torch.equal(buf["actions"][t], acts) and torch.equal(buf["logp"][t], logp)
+        assert torch.equal(buf["rewards"][t], r) and torch.equal(buf["dones"][t].bool(), d)
+    assert torch.equal(buf["obs"][T], b.obs) and torch.equal(a.obs, b.obs) and torch.equal(a.ppos, b.ppos)
+    std = float(np.exp(actor.log_std))
+    assert 0.5 * std < float((buf["actions"] - buf["actions"].mean()).std()) < 10 * std + 1.0
