@@ -48,7 +48,8 @@ class MlpActor:
             raise ValueError("only the reference architecture (8 -> 64 -> 64 -> 1) is supported")
         self.tensors = dict(w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3)
         self.log_std = float(sd["log_std"].reshape(-1)[0]) if "log_std" in sd else 0.0
-        packed = torch.cat([w1.reshape(-1), b1, w2.reshape(-1), b2, w3.reshape(-1), b3.reshape(-1), torch.zeros(3)])
+        packed = torch.cat([w1.reshape(-1), b1, w2.reshape(-1), b2, w3.reshape(-1), b3.reshape(-1),
+                            torch.zeros(3, device=w1.device)])
         assert packed.numel() == POLICY_FLOATS
         self.device = torch.device(device)
         self.packed = packed.contiguous().to(self.device)

@@ -1,0 +1,154 @@
+"""PPO on the batched CUDA environment (BASELINE config 5; the reference's ``training_main.py``).
+
+The reference trains ``stable_baselines3.PPO('MlpPolicy', env, seed=13)`` for 1 048 576 steps of ONE
+environment (``gym_ACAS2D/training_main.py:44-52``; 245 minutes, 71 env-steps/s).  Here the
+rollout side -- actor forward, exploration noise, clipping, environment step, auto-reset -- is one fused
+kernel per step over the whole batch (``BatchedACAS2D.collect_rollout``), and only the learner (GAE,
+clipped surrogate, Adam) is ordinary PyTorch on the same device.  Hyper-parameters are the SB3 1.1.0
+defaults stored in the reference's ``best_model.zip/data``: gamma 0.99, GAE lambda 0.95, clip 0.2,
+10 epochs, lr 3e-4, vf_coef 0.5, ent_coef 0, max_grad_norm 0.5, separate 8-64-64 tanh actor / critic.
+The minibatch is scaled with the batch (SB3 used 64 samples for a 2048-sample rollout, i.e. 32
+minibatches per epoch; the same 32 are used here).
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from gym_ACAS2D.envs import BatchedACAS2D
+from gym_ACAS2D.policy import HIDDEN, OBS_DIM, MlpActor
+
+
+class ActorCritic(nn.Module):
+    """SB3 ``MlpPolicy`` layout (same parameter names as ``policy.pth``)."""
+
+    def __init__(self):
+        super().__init__()
+        self.policy_net = nn.Sequential(nn.Linear(OBS_DIM, HIDDEN), nn.Tanh(), nn.Linear(HIDDEN, HIDDEN), nn.Tanh())
+        self.value_net_body = nn.Sequential(nn.Linear(OBS_DIM, HIDDEN), nn.Tanh(), nn.Linear(HIDDEN, HIDDEN), nn.Tanh())
+        self.action_net = nn.Linear(HIDDEN, 1)
+        self.value_net = nn.Linear(HIDDEN, 1)
+        self.log_std = nn.Parameter(torch.zeros(1))
+        for seq, gain in ((self.policy_net, math.sqrt(2)), (self.value_net_body, math.sqrt(2))):   # SB3 ortho_init
+            for m in seq:
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain)
+                    nn.init.zeros_(m.bias)
+        nn.init.orthogonal_(self.action_net.weight, 0.01); nn.init.zeros_(self.action_net.bias)
+        nn.init.orthogonal_(self.value_net.weight, 1.0); nn.init.zeros_(self.value_net.bias)
+
+    def mean(self, obs):
+        return self.action_net(self.policy_net(obs)).squeeze(-1)
+
+    def value(self, obs):
+        return self.value_net(self.value_net_body(obs)).squeeze(-1)
+
+    def sb3_state_dict(self) -> Dict[str, torch.Tensor]:
+        """Tensors under the names SB3 / ``MlpActor`` use."""
+        p, v = self.policy_net, self.value_net_body
+        return {"log_std": self.log_std.detach(),
+                "mlp_extractor.policy_net.0.weight": p[0].weight.detach(), "mlp_extractor.policy_net.0.bias": p[0].bias.detach(),
+                "mlp_extractor.policy_net.2.weight": p[2].weight.detach(), "mlp_extractor.policy_net.2.bias": p[2].bias.detach(),
+                "mlp_extractor.value_net.0.weight": v[0].weight.detach(), "mlp_extractor.value_net.0.bias": v[0].bias.detach(),
+                "mlp_extractor.value_net.2.weight": v[2].weight.detach(), "mlp_extractor.value_net.2.bias": v[2].bias.detach(),
+                "action_net.weight": self.action_net.weight.detach(), "action_net.bias": self.action_net.bias.detach(),
+                "value_net.weight": self.value_net.weight.detach(), "value_net.bias": self.value_net.bias.detach()}
+
+
+def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device="cuda", seed: int = 13,
+          gamma: float = 0.99, gae_lambda: float = 0.95, clip_range: float = 0.2, n_epochs: int = 10,
+          minibatches: int = 32, lr: float = 3e-4, vf_coef: float = 0.5, ent_coef: float = 0.0,
+          max_grad_norm: float = 0.5, tensor_cores: bool = True, log=print) -> List[Dict[str, float]]:
+    """Train from scratch; returns one record per iteration (episode statistics of that iteration's
+    rollout, timings).  All tensors stay on ``device``."""
+    torch.manual_seed(seed)
+    dev = torch.device(device)
+    env = BatchedACAS2D(num_envs, device=dev, seed=seed, auto_reset=True)
+    env.reset()
+    net = ActorCritic().to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-5)
+    T, B = n_steps, num_envs
+    buffers = None
+    history: List[Dict[str, float]] = []
+    half_log_2pi = 0.5 * math.log(2 * math.pi)
+    for it in range(iterations):
+        # ---- rollout: one fused policy + env kernel per step, written into the [T, B] buffers
+        actor = MlpActor(net.sb3_state_dict(), dev)
+        env.clear_stats()
+        t0 = time.perf_counter()
+        buffers = env.collect_rollout(actor, T, noise_seed=seed, step0=it * T, tensor_cores=tensor_cores, buffers=buffers)
+        torch.cuda.synchronize(dev)
+        t_roll = time.perf_counter() - t0
+        stats = env.episode_stats(reduce=True)
+
+        # ---- GAE (SB3 RolloutBuffer.compute_returns_and_advantage)
+        with torch.no_grad():
+            obs, acts, old_logp = buffers["obs"], buffers["actions"], buffers["logp"]
+            rewards, dones = buffers["rewards"], buffers["dones"].float()
+            values = net.value(obs.reshape(-1, OBS_DIM)).reshape(T + 1, B)
+            adv = torch.zeros(T, B, device=dev)
+            last = torch.zeros(B, device=dev)
+            for t in reversed(range(T)):
+                nonterminal = 1.0 - dones[t]
+                delta = rewards[t] + gamma * values[t + 1] * nonterminal - values[t]
+                last = delta + gamma * gae_lambda * nonterminal * last
+                adv[t] = last
+            returns = adv + values[:T]
+            flat_obs = obs[:T].reshape(-1, OBS_DIM); flat_act = acts.reshape(-1)
+            flat_logp = old_logp.reshape(-1); flat_adv = adv.reshape(-1); flat_ret = returns.reshape(-1)
+
+        # ---- clipped-surrogate updates
+        t0 = time.perf_counter()
+        n = T * B
+        mb = n // minibatches
+        for _ in range(n_epochs):
+            perm = torch.randperm(n, device=dev)
+            for k in range(minibatches):
+                idx = perm[k * mb:(k + 1) * mb]
+                o, a, lp_old, ad, rt = flat_obs[idx], flat_act[idx], flat_logp[idx], flat_adv[idx], flat_ret[idx]
+                ad = (ad - ad.mean()) / (ad.std() + 1e-8)
+                mean = net.mean(o)
+                std = net.log_std.exp()
+                logp = -0.5 * ((a - mean) / std) ** 2 - net.log_std - half_log_2pi
+                ratio = (logp - lp_old).exp()
+                pg = -torch.min(ad * ratio, ad * ratio.clamp(1 - clip_range, 1 + clip_range)).mean()
+                vl = torch.nn.functional.mse_loss(net.value(o), rt)
+                ent = (net.log_std + 0.5 + half_log_2pi).sum()
+                loss = pg + vf_coef * vl - ent_coef * ent
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(net.parameters(), max_grad_norm)
+                opt.step()
+        torch.cuda.synchronize(dev)
+        t_learn = time.perf_counter() - t0
+        rec = dict(iteration=it, env_steps=(it + 1) * n, episodes=stats["episodes"], mean_return=stats["mean_return"],
+                   goal_rate=stats["goal_rate"], collision_rate=stats["collision_rate"], timeout_rate=stats["timeout_rate"],
+                   mean_length=stats["mean_length"], log_std=float(net.log_std.detach()), rollout_s=t_roll, learn_s=t_learn,
+                   rollout_env_steps_per_s=n / t_roll)
+        history.append(rec)
+        if log:
+            log("it {iteration:3d}  steps {env_steps:>10d}  episodes {episodes:6d}  return {mean_return:8.1f}  goal {goal_rate:.3f}  "
+                "coll {collision_rate:.3f}  tout {timeout_rate:.3f}  len {mean_length:6.1f}  log_std {log_std:+.2f}  "
+                "rollout {rollout_s:.3f}s ({rollout_env_steps_per_s:.3g} steps/s)  learn {learn_s:.2f}s".format(**rec))
+    train.last_policy = net
+    return history
+
+
+if __name__ == "__main__":
+    import argparse
+    import json
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--n-steps", type=int, default=128)
+    ap.add_argument("--iterations", type=int, default=20)
+    ap.add_argument("--minibatches", type=int, default=32)
+    ap.add_argument("--fp32", action="store_true", help="CUDA-core float32 actor instead of tcgen05 TF32")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    hist = train(a.envs, a.n_steps, a.iterations, minibatches=a.minibatches, tensor_cores=not a.fp32)
+    if a.out:
+        json.dump(hist, open(a.out, "w"), indent=1)
