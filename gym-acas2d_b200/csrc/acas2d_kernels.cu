@@ -42,8 +42,8 @@ int check_args(const acas2d_params *p, const acas2d_state *s)
     if (!p || !s) return ACAS2D_E_NULL;
     if (p->n_traffic < 1 || p->n_traffic > ACAS2D_MAX_TRAFFIC) return ACAS2D_E_BAD_TRAFFIC;
     if (s->num_envs < 0 || s->num_envs * (int64_t)(5 + 3 * p->n_traffic) > (int64_t)1 << 40) return ACAS2D_E_BAD_SIZE;
-    if (!s->ppos || !s->paux || !s->thot || !s->tres || !s->episode_idx)
-        return ACAS2D_E_NULL;
+    if (s->num_envs > 0 && (!s->ppos || !s->paux || !s->thot || !s->tres || !s->episode_idx))
+        return ACAS2D_E_NULL;                       // an empty batch has nothing to point at
     return 0;
 }
 
@@ -193,12 +193,14 @@ template <int STAGES, int OCC>
 int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
 {
     static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!attr_set[dev & 63]) {                      // function attributes are per device
         cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              STAGES * kStageBytes + 64);
+        attr_set[dev & 63] = true;
     }
     const long long full_tiles = S.B / kTileEnvs;
     long long grid = (long long)sms * OCC;
@@ -309,8 +311,11 @@ inline size_t tiled_warp_bytes(int N, int G)
 
 inline size_t tiled_smem_bytes(int N, int G) { return kTiledWarps * tiled_warp_bytes(N, G); }
 
+#ifndef ACAS2D_TILED_MIN_BLOCKS
+#define ACAS2D_TILED_MIN_BLOCKS 5
+#endif
 template <int G, bool MINSEP>
-__global__ void __launch_bounds__(kTiledWarps * 32)
+__global__ void __launch_bounds__(kTiledWarps * 32, ACAS2D_TILED_MIN_BLOCKS)
 step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
                   const uint32_t magic_n)
 {
@@ -374,6 +379,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         const Float4 *trow = tile + e * TS;
         const double kd = (double)k;
         const bool any_residual = __any_sync(kFull, residual);      // injected float64 states only: keep it a branch
+#pragma unroll 2
         for (int m = 0; m < per_lane; ++m) {
             const Float4 h = trow[j];
             TrafficRec tr;
@@ -829,11 +835,13 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (tensor_cores) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
             cudaFuncSetAttribute(policy_step_n1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
             cudaFuncSetAttribute(policy_step_n1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-            attr_set = true;
+            attr_set[dev & 63] = true;
         }
         long long g = (long long)sms * 4;                   // 4 CTAs/SM: 52 KB smem + 64 TMEM columns each
         const long long t = (S.B + kTcTile - 1) / kTcTile;

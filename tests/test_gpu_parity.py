@@ -296,6 +296,61 @@ def test_properties_at_full_size(cuda):
     assert int(ex_steps.min()) >= 1 and int(ex_steps.max()) <= 1001
 
 
+def test_edge_sizes(cuda):
+    """Empty batch, single env, ragged sizes around the 256-env tile, and the maximum traffic count."""
+    e0 = make(0, 1, auto_reset=True)
+    assert e0.reset().shape == (0, 8)
+    o, r, d = e0.step(torch.zeros(0, device="cuda"))
+    assert o.shape == (0, 8) and r.shape == (0,) and d.shape == (0,)
+    assert e0.episode_stats()["episodes"] == 0
+    for B in (1, 31, 255, 256, 257, 513):
+        a = make(B, 1, seed=2, auto_reset=True); orc = Oracle(1)
+        st = orc.new_state(B); orc.spawn_philox(st, 2, 0); ref0 = orc.observe(st)
+        assert np.abs(npy(a.reset()) - ref0).max() < parity.TOL_OBS_CPA
+        for t in range(5):
+            act = np.full(B, 0.25 * t - 0.5, np.float32)
+            o, r, d = a.step(torch.from_numpy(act).cuda())
+            ro, rr, rf, *_ = orc.vec_step(st, act.astype(np.float64), 2, 0)
+            assert np.abs(npy(o) - ro).max() < parity.TOL_OBS_CPA and np.array_equal(npy(d), rf & FLAG_DONE > 0)
+    from gym_ACAS2D.envs import _native
+    big = make(3, _native.MAX_TRAFFIC, seed=1, auto_reset=True)           # 1024 intruders, obs row of 3077 floats
+    orc = Oracle(_native.MAX_TRAFFIC); st = orc.new_state(3); orc.spawn_philox(st, 1, 0); ref0 = orc.observe(st)
+    assert np.nanmax(np.abs(npy(big.reset()) - ref0)) < parity.TOL_OBS_CPA
+    o, r, d = big.step(torch.zeros(3, device="cuda"))
+    ro, rr, rf, *_ = orc.vec_step(st, np.zeros(3), 1, 0)
+    assert np.nanmax(np.abs(npy(o) - ro)) < parity.TOL_OBS_CPA and np.array_equal(npy(d), rf & FLAG_DONE > 0)
+    with pytest.raises(ValueError):
+        make(4, _native.MAX_TRAFFIC + 1)
+    with pytest.raises(ValueError):
+        make(4, 0)                                                        # Q20: the reference needs >= 1 intruder
+    with pytest.raises(ValueError):
+        make(8, 1).step(torch.zeros(7, device="cuda"))                    # wrong number of actions
+
+
+def test_unclipped_actions_follow_the_reference(cuda):
+    """Q19: the env does not clip actions.  |a| up to 2000 turns the heading by up to 5 revolutions per
+    step (general fmod path of the heading wrap, full-range look-ahead rotation)."""
+    B, T = 512, 60
+    rng = np.random.default_rng(11)
+    pl, tr, steps = _random_states(rng, B, 1)
+    env = make(B, 1, auto_reset=False); env.reset(); env.inject_state(pl, tr, steps)
+    orc = Oracle(1); st = orc.new_state(B)
+    st["player"][:, [0, 1, 3]] = pl; st["player"][:, 2] = 200.0; st["traffic"][:] = tr; st["steps"][:] = steps
+    scale = np.array([1.0, 3.0, 40.0, 400.0, 2000.0])[rng.integers(0, 5, B)]
+    rep = parity.ParityReport()
+    alive = np.ones(B, bool)
+    for t in range(T):
+        a = (rng.uniform(-1, 1, B) * scale).astype(np.float32)
+        obs, rew, done = env.step(torch.from_numpy(a).cuda())
+        o, r, f, oc = orc.step(st, a.astype(np.float64))
+        parity.compare_step(rep, npy(obs), npy(rew), npy(env.flags), o, r, f, alive)
+        alive &= ~(f & FLAG_DONE > 0)
+    assert rep.flag_mismatch == 0 and rep.steps > B * 10, rep
+    ex = env.extract_state()
+    psi_err = np.abs(ex["player"][:, 2] - st["player"][:, 3]); psi_err = np.minimum(psi_err, 360 - psi_err)
+    assert psi_err[alive].max(initial=0) < 1e-9 and np.abs(ex["player"][alive, :2] - st["player"][alive][:, :2]).max(initial=0) < 1e-9
+
+
 def test_timeout_is_exactly_1000_step_calls(cuda):
     """Q5/Q6: an episode is at most 1000 step() calls; final game.steps == 1001, obs[0] == 1.001, and the
     time discount is -0.001 on that step."""

@@ -198,3 +198,23 @@ def test_zero_action_outcome_rates_match_reference_baseline():
     assert c[3] == 0                                     # nobody times out flying straight
     assert 0.50 < c[1] / n < 0.59                        # goal rate (reference spawn rules: 0.546)
     assert 505 < c[4] / n < 545                          # mean game.steps (reference spawn rules: 525.6)
+
+
+def test_unclipped_actions_general_wrap_path():
+    """Q19 on the host build: large |action| exercises wrap360's fmod path and the full-range look-ahead."""
+    rng = np.random.default_rng(3)
+    B = 64
+    hb = HostBatch(B, 1, auto_reset=False)
+    pl = np.c_[rng.uniform(100, 1300, B), rng.uniform(100, 900, B), rng.uniform(0, 360, B)]
+    tr = np.stack([rng.uniform(200, 1580, (B, 1)), rng.uniform(20, 980, (B, 1)), np.full((B, 1), 200.0), rng.uniform(0, 360, (B, 1))], -1)
+    hb.inject_state(pl, tr)
+    orc = Oracle(1); st = orc.new_state(B)
+    st["player"][:, [0, 1, 3]] = pl; st["player"][:, 2] = 200.0; st["traffic"][:] = tr; st["steps"][:] = 1
+    rep = parity.ParityReport(); alive = np.ones(B, bool)
+    for t in range(40):
+        a = (rng.uniform(-1, 1, B) * rng.choice([1.0, 50.0, 800.0, 5000.0], B)).astype(np.float32)
+        obs, rew, _ = hb.step(a)
+        o, r, f, oc = orc.step(st, a.astype(np.float64))
+        parity.compare_step(rep, obs, rew, hb.flags, o, r, f, alive)
+        alive &= ~(f & FLAG_DONE > 0)
+    assert rep.flag_mismatch == 0
