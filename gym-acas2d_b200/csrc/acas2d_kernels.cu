@@ -646,8 +646,8 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
                 float *reward, uint8_t *done, const acas2d_step_aux *aux, void *stream)
 {
     if (int e = check_args(params, state)) return e;
-    if (!actions || !obs || !reward || !done) return ACAS2D_E_NULL;
     if (state->num_envs == 0) return 0;
+    if (!actions || !obs || !reward || !done) return ACAS2D_E_NULL;
     const DevParams P = make_dev_params(*params);
     const StatePtrs S = make_state_ptrs(*state);
     const Sinks out = make_sinks(obs, reward, done, aux);
@@ -724,6 +724,7 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
                      uint8_t *d_done, const acas2d_step_aux *aux, void *stream)
 {
     if (int e = check_args(params, state)) return e;
+    if (state->num_envs == 0) return 0;
     if (!h_actions || !h_obs || !h_reward || !h_done || !d_actions || !d_obs || !d_reward || !d_done)
         return ACAS2D_E_NULL;
     const int64_t B = state->num_envs;
@@ -783,8 +784,8 @@ int acas2d_inject_state(const acas2d_params *params, const acas2d_state *state, 
                         const double *traffic, const int32_t *steps, const double *total_reward, void *stream)
 {
     if (int e = check_args(params, state)) return e;
-    if (!player || !traffic || !steps || !total_reward) return ACAS2D_E_NULL;
     if (state->num_envs == 0) return 0;
+    if (!player || !traffic || !steps || !total_reward) return ACAS2D_E_NULL;
     inject_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
         make_dev_params(*params), make_state_ptrs(*state), player, traffic, steps, total_reward);
     return finish_launch();
@@ -822,8 +823,8 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
 {
     if (int e = check_args(params, state)) return e;
     if (params->n_traffic != 1 || state->min_sep) return ACAS2D_E_BAD_TRAFFIC;    // the trained actor takes 8 inputs
-    if (!weights || !obs_in || !obs_out || !reward || !done) return ACAS2D_E_NULL;
     if (state->num_envs == 0) return 0;
+    if (!weights || !obs_in || !obs_out || !reward || !done) return ACAS2D_E_NULL;
     const DevParams P = make_dev_params(*params);
     const StatePtrs S = make_state_ptrs(*state);
     const Sinks out = make_sinks(obs_out, reward, done, aux);

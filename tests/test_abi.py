@@ -58,7 +58,10 @@ def test_argument_errors_do_not_touch_the_device(lib):
     assert lib.acas2d_params_default(ctypes.byref(_native.Params()), 0) == -2            # N_TRAFFIC = 0 (Q20)
     assert lib.acas2d_params_default(ctypes.byref(_native.Params()), _native.MAX_TRAFFIC + 1) == -2
     assert lib.acas2d_step(None, None, None, None, None, None, None, None) == -1
+    s.num_envs = 4
     assert lib.acas2d_reset(ctypes.byref(p), ctypes.byref(s), None, None, None) == -1    # state pointers NULL
+    s.num_envs = 0
+    assert lib.acas2d_reset(ctypes.byref(p), ctypes.byref(s), None, None, None) == 0     # empty batch: nothing to do
     s.num_envs = -5
     assert lib.acas2d_reset(ctypes.byref(p), ctypes.byref(s), None, None, None) == -3
     p.n_traffic = 0
