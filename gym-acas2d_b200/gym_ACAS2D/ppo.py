@@ -59,10 +59,71 @@ class ActorCritic(nn.Module):
                 "value_net.weight": self.value_net.weight.detach(), "value_net.bias": self.value_net.bias.detach()}
 
 
+class _GraphedUpdate:
+    """One PPO gradient step (gather minibatch, losses, backward, grad clip, Adam) as a CUDA graph."""
+
+    def __init__(self, net, opt, flat_obs, flat_act, flat_logp, n, mb, clip_range, vf_coef, ent_coef, max_grad_norm,
+                 use_graph=True):
+        dev = flat_obs.device
+        self.net, self.opt = net, opt
+        self.obs, self.act, self.logp = flat_obs, flat_act, flat_logp          # views of the reused rollout buffers
+        self.adv = torch.zeros(n, device=dev); self.ret = torch.zeros(n, device=dev)
+        self.idx = torch.zeros(mb, dtype=torch.long, device=dev)
+        self.cfg = (clip_range, vf_coef, ent_coef, max_grad_norm)
+        self.graph = None
+        if use_graph:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                state = ([p.detach().clone() for p in net.parameters()], opt.state_dict())
+                for _ in range(3):                                              # warm-up (allocations, Adam state)
+                    self._body()
+                with torch.no_grad():                                           # the warm-up must not train
+                    for p, q in zip(net.parameters(), state[0]):
+                        p.copy_(q)
+                for st in opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph):
+                self._body()
+
+    def _body(self):
+        clip_range, vf_coef, ent_coef, max_grad_norm = self.cfg
+        net, idx = self.net, self.idx
+        o, a, lp_old, ad, rt = self.obs[idx], self.act[idx], self.logp[idx], self.adv[idx], self.ret[idx]
+        ad = (ad - ad.mean()) / (ad.std() + 1e-8)
+        mean = net.mean(o)
+        logp = -0.5 * ((a - mean) / net.log_std.exp()) ** 2 - net.log_std - 0.5 * math.log(2 * math.pi)
+        ratio = (logp - lp_old).exp()
+        pg = -torch.min(ad * ratio, ad * ratio.clamp(1 - clip_range, 1 + clip_range)).mean()
+        vl = torch.nn.functional.mse_loss(net.value(o), rt)
+        ent = (net.log_std + 0.5 + 0.5 * math.log(2 * math.pi)).sum()
+        loss = pg + vf_coef * vl - ent_coef * ent
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        nn.utils.clip_grad_norm_(net.parameters(), max_grad_norm)
+        self.opt.step()
+
+    def load(self, adv, ret):
+        self.adv.copy_(adv); self.ret.copy_(ret)
+
+    def step(self, idx):
+        self.idx.copy_(idx)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+
+
 def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device="cuda", seed: int = 13,
           gamma: float = 0.99, gae_lambda: float = 0.95, clip_range: float = 0.2, n_epochs: int = 10,
           minibatches: int = 32, lr: float = 3e-4, vf_coef: float = 0.5, ent_coef: float = 0.0,
-          max_grad_norm: float = 0.5, tensor_cores: bool = True, log=print) -> List[Dict[str, float]]:
+          max_grad_norm: float = 0.5, tensor_cores: bool = True, cuda_graph: bool = True,
+          log=print) -> List[Dict[str, float]]:
     """Train from scratch; returns one record per iteration (episode statistics of that iteration's
     rollout, timings).  All tensors stay on ``device``."""
     torch.manual_seed(seed)
@@ -70,11 +131,11 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
     env = BatchedACAS2D(num_envs, device=dev, seed=seed, auto_reset=True)
     env.reset()
     net = ActorCritic().to(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-5)
+    opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-5, capturable=True)
     T, B = n_steps, num_envs
     buffers = None
+    upd = None
     history: List[Dict[str, float]] = []
-    half_log_2pi = 0.5 * math.log(2 * math.pi)
     for it in range(iterations):
         # ---- rollout: one fused policy + env kernel per step, written into the [T, B] buffers
         actor = MlpActor(net.sb3_state_dict(), dev)
@@ -101,28 +162,20 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
             flat_obs = obs[:T].reshape(-1, OBS_DIM); flat_act = acts.reshape(-1)
             flat_logp = old_logp.reshape(-1); flat_adv = adv.reshape(-1); flat_ret = returns.reshape(-1)
 
-        # ---- clipped-surrogate updates
+        # ---- clipped-surrogate updates: one CUDA-graph replay per gradient step (the eager step is
+        #      ~60 tiny kernels, i.e. host-launch-bound); the graph reads the rollout through static
+        #      storages (the [T, B] buffers are reused) and a static index tensor
         t0 = time.perf_counter()
         n = T * B
         mb = n // minibatches
+        if upd is None:
+            upd = _GraphedUpdate(net, opt, flat_obs, flat_act, flat_logp, n, mb, clip_range, vf_coef, ent_coef,
+                                 max_grad_norm, use_graph=cuda_graph)
+        upd.load(flat_adv, flat_ret)
         for _ in range(n_epochs):
             perm = torch.randperm(n, device=dev)
             for k in range(minibatches):
-                idx = perm[k * mb:(k + 1) * mb]
-                o, a, lp_old, ad, rt = flat_obs[idx], flat_act[idx], flat_logp[idx], flat_adv[idx], flat_ret[idx]
-                ad = (ad - ad.mean()) / (ad.std() + 1e-8)
-                mean = net.mean(o)
-                std = net.log_std.exp()
-                logp = -0.5 * ((a - mean) / std) ** 2 - net.log_std - half_log_2pi
-                ratio = (logp - lp_old).exp()
-                pg = -torch.min(ad * ratio, ad * ratio.clamp(1 - clip_range, 1 + clip_range)).mean()
-                vl = torch.nn.functional.mse_loss(net.value(o), rt)
-                ent = (net.log_std + 0.5 + half_log_2pi).sum()
-                loss = pg + vf_coef * vl - ent_coef * ent
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                nn.utils.clip_grad_norm_(net.parameters(), max_grad_norm)
-                opt.step()
+                upd.step(perm[k * mb:(k + 1) * mb])
         torch.cuda.synchronize(dev)
         t_learn = time.perf_counter() - t0
         rec = dict(iteration=it, env_steps=(it + 1) * n, episodes=stats["episodes"], mean_return=stats["mean_return"],
