@@ -66,11 +66,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, unsigned parity)
     } while (!ok);
 }
 
-// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gmem_src, unsigned bytes, uint32_t bar)
+#ifndef ACAS2D_LOAD_HINT
+#define ACAS2D_LOAD_HINT 1      /* L2 evict-first cache hint on the TMA loads: the records are rewritten, not re-read (90.8 vs 91.6 us) */
+#endif
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gmem_src, unsigned bytes, uint32_t bar,
+                                            uint64_t policy = 0)
+{
+#if ACAS2D_LOAD_HINT
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+#else
+    (void)policy;
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+#endif
 }
 
 }  // namespace acas2d

@@ -120,14 +120,15 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
     __syncthreads();
 
     const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full);
+    const uint64_t pol = ACAS2D_LOAD_HINT ? l2_evict_first_policy() : 0;
     auto issue = [&](long long tile, int s) {
         const uint32_t base = smem_base + s * kStageBytes, bar = full_base + 8 * s;
         const long long e0 = tile * kTileEnvs;
         mbar_expect_tx(bar, kStageBytes);
-        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, bar);
-        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, bar);
-        tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar);
-        tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, bar);
+        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, bar, pol);
+        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, bar, pol);
+        tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar, pol);
+        tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, bar, pol);
     };
 
     if (tid == 0) {

@@ -91,7 +91,6 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     float *sB1 = (float *)(smem + kTcB1), *sB2 = (float *)(smem + kTcB2), *sVec = (float *)(smem + kTcVec);
-    uint64_t *bar = (uint64_t *)(smem + kTcBar);
     uint32_t *tmem_slot = (uint32_t *)(smem + kTcBar + 8);
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t bar_addr = smem_base + kTcBar;
