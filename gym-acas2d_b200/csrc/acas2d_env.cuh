@@ -479,6 +479,31 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     if (S.min_sep) S.min_sep[i] = minsep;
 }
 
+// game.observe() WITHOUT the steps increment (game.py:199-220): the observation row of the state as it
+// stands, with the player's last lateral acceleration taken as 0 (what it is right after a reset or an
+// injection; the state does not keep the previous action).
+ACAS_HD void observe_env(const DevParams &P, const StatePtrs &S, int64_t i, float *obs)
+{
+    const int N = P.n_traffic;
+    const int L = 5 + 3 * N;
+    const Vec2d pp = S.ppos[i];
+    const PlayerAux pa = S.paux[i];
+    const int st = pa.steps & kStepsMask;
+    Player p;
+    p.x = pp.x; p.y = pp.y;
+    player_set_heading(P, p, pa.psi, 0.0);
+    const PlayerView v = player_view(P, p, st);
+    float *row = obs + (int64_t)L * i;
+    for (int q = 0; q < 5; ++q) row[q] = v.obs[q];
+    for (int j = 0; j < N; ++j) {
+        const TrafficRec tr = traffic_load(S, i * N + j, (pa.steps & kResidualBit) != 0);
+        const Encounter en = encounter(P, p, intruder_at(P, tr, (double)(st - 1)));
+        row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
+        row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
+        row[5 + 3 * j + 2] = en.v_c * P.vc_scale;
+    }
+}
+
 ACAS_HD void inject_env(const DevParams &P, const StatePtrs &S, int64_t i, const double *player,
                         const double *traffic, const int32_t *steps, const double *total_reward)
 {

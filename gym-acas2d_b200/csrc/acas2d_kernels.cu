@@ -575,6 +575,13 @@ extract_kernel(const DevParams P, const StatePtrs S, double *__restrict__ player
 }
 
 __global__ void __launch_bounds__(kBlock)
+observe_kernel(const DevParams P, const StatePtrs S, float *__restrict__ obs)
+{
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < S.B) observe_env(P, S, i, obs);
+}
+
+__global__ void __launch_bounds__(kBlock)
 random_actions_kernel(int64_t B, uint64_t gid0, uint64_t action_seed, uint64_t step_index, float *__restrict__ actions)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -799,6 +806,16 @@ int acas2d_extract_state(const acas2d_params *params, const acas2d_state *state,
     if (state->num_envs == 0) return 0;
     extract_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
         make_dev_params(*params), make_state_ptrs(*state), player, traffic, steps, total_reward);
+    return finish_launch();
+}
+
+int acas2d_observe(const acas2d_params *params, const acas2d_state *state, float *obs, void *stream)
+{
+    if (int e = check_args(params, state)) return e;
+    if (state->num_envs == 0) return 0;
+    if (!obs) return ACAS2D_E_NULL;
+    observe_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
+        make_dev_params(*params), make_state_ptrs(*state), obs);
     return finish_launch();
 }
 

@@ -300,6 +300,16 @@ class BatchedACAS2D:
             torch.cuda.current_stream(dev).synchronize()            # staging tensors die with this frame
         self.launches += 1
 
+    def observe(self) -> torch.Tensor:
+        """Observation rows of the games as they stand (no step, no ``steps`` increment; last lateral
+        acceleration taken as 0): the reset observation of a freshly injected state.  Written into and
+        returned as the ``obs`` buffer."""
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_observe(self._p(), self._s(), self.obs.data_ptr(), self._stream()),
+                          "acas2d_observe")
+        self.launches += 1
+        return self.obs
+
     def extract_state(self) -> Dict[str, np.ndarray]:
         """Current games as numpy float64: player [B,3], traffic [B,N,4], steps, total_reward, episode_idx."""
         B, N, dev = self.num_envs, self.n_traffic, self.device

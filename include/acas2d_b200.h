@@ -174,6 +174,11 @@ int acas2d_extract_state(const acas2d_params *params, const acas2d_state *state,
                          double *player, double *traffic,
                          int32_t *steps, double *total_reward, void *stream);
 
+/* Observation rows float[B][L] of the games as they stand (game.observe, game.py:194-220, without its
+ * steps increment and with the player's last lateral acceleration taken as 0 -- i.e. exactly the
+ * reset observation for a state injected at steps == 1).  Does not modify the state. */
+int acas2d_observe(const acas2d_params *params, const acas2d_state *state, float *obs, void *stream);
+
 /* Synthetic benchmark path: K consecutive auto-resetting steps per launch with actions
  * drawn in-kernel, a ~ U(-1,1) from Philox(key = action_seed, counter = (global env id,
  * step0 + k)).  State stays in registers between the K steps; nothing but the state, the

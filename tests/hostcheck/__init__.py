@@ -42,6 +42,7 @@ class HostBatch:
         self.lib.hostcheck_rollout_random.argtypes = [PP, SP, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, vp]
         self.lib.hostcheck_random_actions.argtypes = [SP, ctypes.c_uint64, ctypes.c_uint64, vp]
         self.lib.hostcheck_inject.argtypes = [PP, SP, vp, vp, vp, vp]
+        self.lib.hostcheck_observe.argtypes = [PP, SP, vp]
         self.lib.hostcheck_extract.argtypes = [PP, SP, vp, vp, vp, vp]
         self.lib.hostcheck_wrap360.argtypes = [ctypes.c_double]
         self.lib.hostcheck_wrap360.restype = ctypes.c_double
@@ -93,6 +94,10 @@ class HostBatch:
         st = np.ones(B, np.int32) if steps is None else np.ascontiguousarray(steps, np.int32)
         tot = np.zeros(B) if total_reward is None else np.ascontiguousarray(total_reward, np.float64)
         self.lib.hostcheck_inject(ctypes.byref(self.params), ctypes.byref(self._state), _p(pl), _p(tr), _p(st), _p(tot))
+
+    def observe(self):
+        self.lib.hostcheck_observe(ctypes.byref(self.params), ctypes.byref(self._state), _p(self.obs))
+        return self.obs
 
     def extract_state(self):
         B, N = self.num_envs, self.n_traffic

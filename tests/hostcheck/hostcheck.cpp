@@ -110,6 +110,14 @@ int hostcheck_random_actions(const acas2d_state *s, uint64_t action_seed, uint64
     return 0;
 }
 
+int hostcheck_observe(const acas2d_params *p, const acas2d_state *s, float *obs)
+{
+    const DevParams P = make_dev_params(*p);
+    const StatePtrs S = make_state_ptrs(*s);
+    for (int64_t i = 0; i < S.B; ++i) observe_env(P, S, i, obs);
+    return 0;
+}
+
 int hostcheck_inject(const acas2d_params *p, const acas2d_state *s, const double *player, const double *traffic,
                      const int32_t *steps, const double *total_reward)
 {

@@ -481,3 +481,43 @@ def test_vec_env_adapter_semantics(cuda):
     assert venv.env_is_wrapped(object) == [False] * B and venv.get_attr("num_envs")[0] == B
     s = venv.core.episode_stats()
     assert s["episodes"] == seen and s["timeout"] == 0
+
+
+def test_golden_csv_replayed_on_the_gpu(cuda, golden_dir):
+    """The reference's own golden artefact, through the CUDA path: the 100 zero-action episodes of
+    baseline_ACAS2D_PPO_11_100.csv, spawned with the reference's draw order on MT19937 (seed 13, two
+    discarded games) and injected, then recorded in the reference's CSV schema by records.record_episodes.
+    Outcome and Time Steps bit-exact for 100/100, paths within 1e-9 px, total reward within 5e-3."""
+    import random
+    from gym_ACAS2D import records
+    from oracle.acas2d_oracle import DEFAULTS, reference_spawn
+    g = np.load(os.path.join(golden_dir, "baseline_zero_action.npz"))
+    rng = random.Random(13)
+    for _ in range(2):
+        reference_spawn(rng, DEFAULTS)
+    spawns = [reference_spawn(rng, DEFAULTS) for _ in range(100)]
+    player = np.array([[s[0][0], s[0][1], s[0][3]] for s in spawns]); traffic = np.array([s[1] for s in spawns])
+    env = make(100, 1, auto_reset=False)
+    rows = records.record_episodes(env, start=(player, traffic))
+    names = {1: "Goal", 2: "Collision", 3: "Timeout"}
+    stride = int(g["stride"])
+    for ep, row in enumerate(rows):
+        assert row["Outcome"] == names[int(g["outcome"][ep])], ep
+        assert row["Time Steps"] == g["time_steps"][ep], ep
+        path = np.array(row["Path"]); tpath = np.array(row["Traffic Paths"][0])
+        assert len(path) == g["path_len"][ep] and len(tpath) == len(path), ep
+        n = len(path[::stride])
+        assert np.abs(path[::stride] - g["path_samples"][ep][:n]).max() < 1e-9, ep
+        assert np.abs(tpath[::stride] - g["traffic_samples"][ep][:n]).max() < 1e-9, ep
+        assert np.array_equal(tpath[0], tpath[1])                                   # Q10
+        assert abs(row["Total Reward"] - g["total_reward"][ep]) < parity.TOL_RETURN, ep
+        assert row["Path Length"] == pytest.approx(2.0 * (row["Time Steps"] - 1))
+        assert len(row["psi"]) == len(path) and len(row["r_step"]) == len(path)
+    assert sum(r["Outcome"] == "Collision" for r in rows) == 58 and sum(r["Outcome"] == "Goal" for r in rows) == 42
+    import tempfile, pandas as pd
+    with tempfile.TemporaryDirectory() as d:
+        records.to_csv(rows[:3], os.path.join(d, "t.csv"))
+        df = pd.read_csv(os.path.join(d, "t.csv"))
+        assert list(df.columns) == records.TESTING_COLUMNS and len(df) == 3
+        records.to_csv(rows[:3], os.path.join(d, "b.csv"), records.BASELINE_COLUMNS)
+        assert list(pd.read_csv(os.path.join(d, "b.csv")).columns) == records.BASELINE_COLUMNS

@@ -218,3 +218,21 @@ def test_unclipped_actions_general_wrap_path():
         parity.compare_step(rep, obs, rew, hb.flags, o, r, f, alive)
         alive &= ~(f & FLAG_DONE > 0)
     assert rep.flag_mismatch == 0
+
+
+def test_observe_is_the_reset_observation_of_an_injected_state():
+    """acas2d_observe: game.observe() without the counter increment == the oracle's observe() of the same state."""
+    rng = np.random.default_rng(5)
+    B, N = 40, 3
+    hb = HostBatch(B, N, auto_reset=False)
+    pl = np.c_[rng.uniform(0, 1600, B), rng.uniform(0, 1000, B), rng.uniform(0, 360, B)]
+    tr = np.stack([rng.uniform(0, 1600, (B, N)), rng.uniform(0, 1000, (B, N)), np.full((B, N), 200.0), rng.uniform(0, 360, (B, N))], -1)
+    steps = rng.integers(1, 900, B).astype(np.int32)
+    hb.inject_state(pl, tr, steps)
+    orc = Oracle(N); st = orc.new_state(B)
+    st["player"][:, [0, 1, 3]] = pl; st["player"][:, 2] = 200.0; st["traffic"][:] = tr; st["steps"][:] = steps - 1
+    ref = orc.observe(st)                               # increments to `steps`
+    got = hb.observe().astype(np.float64)
+    assert np.abs(got[:, :5] - ref[:, :5]).max() < parity.TOL_OBS_BASE
+    assert np.nanmax(np.abs(got[:, 5:] - ref[:, 5:])) < parity.TOL_OBS_CPA
+    assert np.array_equal(hb.extract_state()["steps"], steps)       # state untouched
