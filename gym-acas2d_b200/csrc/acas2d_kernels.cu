@@ -12,7 +12,10 @@
 //                         any-collision reduced with warp shuffles, observation rows
 //                         assembled in shared memory and written back coalesced.
 //   rollout_n1_kernel     K fused steps with in-kernel Philox actions (synthetic benchmark).
-//   reset / inject / extract / random_actions  small utility kernels.
+//   policy_step_n1_kernel / policy_step_n1_tc_kernel (acas2d_policy*.cuh)
+//                         the reference agent's actor MLP fused with the env step: float32 on the
+//                         CUDA cores, or tcgen05 TF32 MMAs with TMEM accumulators.
+//   reset / observe / inject / extract / random_actions  small utility kernels.
 //
 // There is no CPU fallback in this file: every entry point launches on the device.
 #include <cuda_runtime.h>
