@@ -201,6 +201,29 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host buffer is allocated, so the
+    end-to-end path's H2D / D2H copies do not cross sockets (8 ranks on one node otherwise pile up)."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -214,6 +237,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a GPU: the ACAS-2D step has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -353,7 +377,8 @@ def run_ours(args):
                              "note": "per GPU; achieved = A(N) x envs per launch / CUDA-event time per launch"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": (4 * L + 5) * B,
                         "steps": Ke, "ms_per_step": ms_e2e / Ke,
-                        "path": "BatchedACAS2D.step_host -> acas2d_step_host (pinned host buffers)"},
+                        "path": "BatchedACAS2D.step_host -> acas2d_step_host (pinned host buffers)",
+                        "numa_node_rank0": numa},
                 "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "launch_mode": f"CUDA graph, {GK} step kernels per replay x {replays} replays + {rest} eager steps",
                 "eager": {"ms_per_step": ms_eager / max(1, eager_launches), "launches": int(eager_launches),
