@@ -144,28 +144,41 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             r.o0 = make_float4(0.f, 0.f, 0.f, 0.f); r.o1 = r.o0;
         }
     };
-    Rec nxt;
-    fetch((int64_t)blockIdx.x * kTcTile + tid, nxt);
-
-    for (int64_t base = (int64_t)blockIdx.x * kTcTile; base < S.B; base += (int64_t)gridDim.x * kTcTile) {
-        const int64_t i = base + tid;
-        const bool valid = i < S.B;
-        const Rec cur = nxt;
-        fetch(i + (int64_t)gridDim.x * kTcTile, nxt);
-
-        // ---- A1 <- this env's observation row (two 16-byte chunks)
-        *(float4 *)(smem + kTcA1 + tid * 16) = cur.o0;
-        *(float4 *)(smem + kTcA1 + 2048 + tid * 16) = cur.o1;
+    const int64_t stride = (int64_t)gridDim.x * kTcTile;
+    auto stage_obs = [&](const Rec &r) {                 // A1 <- this env's observation row (two 16-byte chunks)
+        *(float4 *)(smem + kTcA1 + tid * 16) = r.o0;
+        *(float4 *)(smem + kTcA1 + 2048 + tid * 16) = r.o1;
+    };
+    auto sync_for_mma = [&]() {                          // smem writes -> async proxy; orders prior tcgen05.ld
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");          // also orders last tile's tcgen05.ld
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-
-        // ---- layer 1 on the tensor cores
+    };
+    auto issue_layer1 = [&]() {
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             umma_tf32(tmem_base, a1_desc, b1_desc, idesc, 0u);
             umma_commit(bar_addr);
         }
+    };
+
+    // Prologue: first tile's records, its layer 1 in flight, second tile's records requested.
+    int64_t base = (int64_t)blockIdx.x * kTcTile;
+    bool have = base < S.B;
+    Rec cur, nxt;
+    fetch(base + tid, cur);
+    fetch(base + stride + tid, nxt);
+    if (have) {
+        stage_obs(cur);
+        sync_for_mma();
+        issue_layer1();
+    }
+
+    while (have) {
+        const int64_t i = base + tid;
+        const bool valid = i < S.B;
+
+        // ---- layer 1 was issued one stage ago (behind the previous tile's env step)
         mbar_wait(bar_addr, phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -186,9 +199,7 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
                 *(float4 *)(smem + kTcA2 + (half * 8 + c) * 2048 + tid * 16) = h;
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        sync_for_mma();
 
         // ---- layer 2 on the tensor cores: eight K = 8 slices accumulate into D2
         if (tid == 0) {
@@ -203,7 +214,7 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- epilogue 2: mean = w3 . tanh(D2 + b2) + b3, sample, clip, env step
+        // ---- epilogue 2: mean = w3 . tanh(D2 + b2) + b3
         float mean = sVec[192];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -219,6 +230,21 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
                 mean = fmaf(w.w, tanh_mufu(v[c * 4 + 3] + b.w), mean);
             }
         }
+
+        // ---- next tile: its observation rows go to A1 (D2 and A2 are drained) and its layer 1 is issued
+        //      NOW, so that the tensor-core round trip runs behind this tile's env step
+        const int64_t next_base = base + stride;
+        const bool have_next = next_base < S.B;
+        const Vec2d pp = cur.pp; const PlayerAux pa = cur.pa; const Float4 h = cur.h;
+        cur = nxt;
+        if (have_next) {
+            fetch(next_base + stride + tid, nxt);
+            stage_obs(cur);
+            sync_for_mma();
+            issue_layer1();
+        }
+
+        // ---- sample, clip, env step of this tile
         if (valid) {
             float a = mean;
             if (STOCHASTIC) {
@@ -229,10 +255,10 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             if (actions_out) actions_out[i] = a;
             const float clipped = fminf(1.0f, fmaxf(-1.0f, a));
             Env1 e;
-            e.px = cur.pp.x; e.py = cur.pp.y; e.psi = cur.pa.psi; e.ret = cur.pa.ep_return;
-            e.steps = cur.pa.steps & kStepsMask;
-            e.residual = (cur.pa.steps & kResidualBit) != 0;
-            e.tr.x0 = (double)cur.h.x; e.tr.y0 = (double)cur.h.y; e.tr.psi = (double)cur.h.z; e.tr.v = (double)cur.h.w;
+            e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.ret = pa.ep_return;
+            e.steps = pa.steps & kStepsMask;
+            e.residual = (pa.steps & kResidualBit) != 0;
+            e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
             if (__builtin_expect(e.residual, 0)) {
                 const Residual r = S.tres[i];
                 e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
@@ -242,6 +268,8 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             step_env1<false, true>(P, S, e, clipped, i, out, tally, nullptr);
             store_env1(S, i, e, false);
         }
+        base = next_base;
+        have = have_next;
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
