@@ -44,7 +44,6 @@ struct StatePtrs {
     Vec2d *ppos;
     PlayerAux *paux;
     Float4 *thot;
-    int rec_f4;             // float4 words per intruder record: 1 (N_TRAFFIC == 1) or 2 (record carries dx, dy)
     Residual *tres;
     uint32_t *episode_idx;
     float *min_sep;
@@ -117,10 +116,9 @@ inline DevParams make_dev_params(const acas2d_params &p)
     return d;
 }
 
-inline StatePtrs make_state_ptrs(const acas2d_state &s, int n_traffic)
+inline StatePtrs make_state_ptrs(const acas2d_state &s)
 {
     StatePtrs o;
-    o.rec_f4 = ACAS2D_TRAFFIC_RECORD_FLOATS(n_traffic) / 4;
     o.ppos = (Vec2d *)s.ppos;
     o.paux = (PlayerAux *)s.paux;
     o.thot = (Float4 *)s.thot;
@@ -163,20 +161,13 @@ ACAS_HD void tally_add(Tally &t, int outcome, int steps, float ep_return, float 
 // record is exact; injected float64 states keep their remainder in the cold Residual array and
 // set kResidualBit in PlayerAux.steps.  The intruder flies a straight line (game.py:243-245,
 // a_lat == 0): position after k moves = origin + k * (v cos psi dt, v sin psi dt), in float64.
-struct TrafficRec { double x0, y0, psi, v, dx, dy; bool has_vel; };
+struct TrafficRec { double x0, y0, psi, v; };
 
 ACAS_HD TrafficRec traffic_load(const StatePtrs &S, int64_t ij, bool residual)
 {
-    const Float4 h = S.thot[ij * S.rec_f4];
+    const Float4 h = S.thot[ij];
     TrafficRec t;
     t.x0 = (double)h.x; t.y0 = (double)h.y; t.psi = (double)h.z; t.v = (double)h.w;
-    t.has_vel = S.rec_f4 == 2;
-    if (t.has_vel) {                                                  // N_TRAFFIC > 1: cached displacement per step
-        const Vec2d vel = *(const Vec2d *)(S.thot + ij * 2 + 1);
-        t.dx = vel.x; t.dy = vel.y;
-    } else {
-        t.dx = 0.0; t.dy = 0.0;
-    }
     if (residual) {
         const Residual r = S.tres[ij];
         t.x0 += r.x0; t.y0 += r.y0; t.psi += r.psi; t.v += r.v;      // exact: r = full - float(full)
@@ -184,20 +175,12 @@ ACAS_HD TrafficRec traffic_load(const StatePtrs &S, int64_t ij, bool residual)
     return t;
 }
 
-// Writes the hot record (and, for the 32-byte layout, the float64 displacement per step, which it also
-// leaves in `t` for the caller).  Returns true when the record is not float32-representable.
-ACAS_HD bool traffic_store(const DevParams &P, const StatePtrs &S, int64_t ij, TrafficRec &t, bool write_residual)
+// Returns true when the record needed a residual (i.e. was not float32-representable).
+ACAS_HD bool traffic_store(const StatePtrs &S, int64_t ij, const TrafficRec &t, bool write_residual)
 {
     Float4 h;
     h.x = (float)t.x0; h.y = (float)t.y0; h.z = (float)t.psi; h.w = (float)t.v;
-    S.thot[ij * S.rec_f4] = h;
-    t.has_vel = S.rec_f4 == 2;
-    if (t.has_vel) {
-        Vec2d vel;
-        heading_to_velocity(P, t.v, t.psi, &vel.x, &vel.y);
-        *(Vec2d *)(S.thot + ij * 2 + 1) = vel;
-        t.dx = vel.x; t.dy = vel.y;
-    }
+    S.thot[ij] = h;
     Residual r;
     r.x0 = t.x0 - (double)h.x; r.y0 = t.y0 - (double)h.y; r.psi = t.psi - (double)h.z; r.v = t.v - (double)h.w;
     const bool need = r.x0 != 0.0 || r.y0 != 0.0 || r.psi != 0.0 || r.v != 0.0;
@@ -208,8 +191,7 @@ ACAS_HD bool traffic_store(const DevParams &P, const StatePtrs &S, int64_t ij, T
 ACAS_HD Intruder intruder_at(const DevParams &P, const TrafficRec &t, double k)
 {
     Intruder it;
-    if (t.has_vel) { it.dx = t.dx; it.dy = t.dy; }
-    else heading_to_velocity(P, t.v, t.psi, &it.dx, &it.dy);
+    heading_to_velocity(P, t.v, t.psi, &it.dx, &it.dy);
     it.x = t.x0 + k * it.dx;
     it.y = t.y0 + k * it.dy;
     it.vratio = P.uniform_speed ? 1.0 : P.airspeed / t.v;              // Q3
@@ -228,7 +210,6 @@ ACAS_HD TrafficRec spawn_traffic(const DevParams &P, uint64_t seed, uint64_t gid
     }
     t.x0 = (double)(float)t.x0; t.y0 = (double)(float)t.y0;
     t.psi = (double)(float)t.psi; t.v = (double)(float)t.v;
-    t.dx = 0.0; t.dy = 0.0; t.has_vel = false;
     return t;
 }
 
@@ -351,7 +332,7 @@ ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
     e.respawned = false;
 }
 
-ACAS_HD void store_env1(const DevParams &P, const StatePtrs &S, int64_t i, const Env1 &e, bool minsep)
+ACAS_HD void store_env1(const StatePtrs &S, int64_t i, const Env1 &e, bool minsep)
 {
     Vec2d pp; pp.x = e.px; pp.y = e.py;
     PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps | (e.residual ? kResidualBit : 0); pa.ep_return = e.ret;
@@ -361,7 +342,7 @@ ACAS_HD void store_env1(const DevParams &P, const StatePtrs &S, int64_t i, const
         ACAS_ST_POLICY(ACAS2D_STATE_STORE, (Float4 *)(S.ppos + i), a);
         ACAS_ST_POLICY(ACAS2D_STATE_STORE, (Float4 *)(S.paux + i), b);
     }
-    if (e.respawned) { TrafficRec tr = e.tr; traffic_store(P, S, i, tr, false); }
+    if (e.respawned) traffic_store(S, i, e.tr, false);
     if (minsep) S.min_sep[i] = e.minsep;
 }
 
@@ -444,8 +425,8 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             for (int q = 0; q < 5; ++q) row[q] = v1.obs[q];
             minsep = INFINITY;
             for (int j = 0; j < N; ++j) {
-                TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
-                traffic_store(P, S, i * N + j, tr, false);
+                const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
+                traffic_store(S, i * N + j, tr, false);
                 const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
                 minsep = fminf(minsep, en.d);
                 row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
@@ -481,8 +462,8 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     if (row) for (int q = 0; q < 5; ++q) row[q] = v.obs[q];
     float minsep = INFINITY;
     for (int j = 0; j < N; ++j) {
-        TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
-        traffic_store(P, S, i * N + j, tr, false);
+        const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
+        traffic_store(S, i * N + j, tr, false);
         const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
         minsep = fminf(minsep, en.d);
         if (row) {
@@ -535,13 +516,12 @@ ACAS_HD void inject_env(const DevParams &P, const StatePtrs &S, int64_t i, const
     for (int j = 0; j < N; ++j) {
         const int64_t ij = i * N + j;
         TrafficRec tr;
-        tr.dx = 0.0; tr.dy = 0.0; tr.has_vel = false;
         const double x = traffic[4 * ij], y = traffic[4 * ij + 1];
         tr.v = traffic[4 * ij + 2]; tr.psi = traffic[4 * ij + 3];
         double dx, dy;
         heading_to_velocity(P, tr.v, tr.psi, &dx, &dy);
         tr.x0 = x - back * dx; tr.y0 = y - back * dy;               // closed-form origin (steps == 1)
-        residual |= traffic_store(P, S, ij, tr, true);
+        residual |= traffic_store(S, ij, tr, true);
         const double ox = x - np.x, oy = y - np.y;
         minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
     }

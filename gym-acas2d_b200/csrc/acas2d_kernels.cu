@@ -88,7 +88,7 @@ step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ a
         load_env1(S, i, e, MINSEP);
         const float a = __ldcs(actions + i);
         step_env1<MINSEP, true>(P, S, e, a, i, out, tally, nullptr);
-        store_env1(P, S, i, e, MINSEP);
+        store_env1(S, i, e, MINSEP);
     }
     tally_flush_warp(S.stats, tally);
 }
@@ -176,7 +176,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         e.minsep = 0.0f;
         e.respawned = false;
         step_env1<false, true>(P, S, e, a, i, out, tally, nullptr);
-        store_env1(P, S, i, e, false);
+        store_env1(S, i, e, false);
     }
 
     // ragged tail (B % 256 envs): one CTA, plain loads
@@ -187,7 +187,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
             Env1 e;
             load_env1(S, i, e, false);
             step_env1<false, true>(P, S, e, __ldcs(actions + i), i, out, tally, nullptr);
-            store_env1(P, S, i, e, false);
+            store_env1(S, i, e, false);
         }
     }
     tally_flush_warp(S.stats, tally);
@@ -246,7 +246,7 @@ policy_step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restr
             Env1 e;
             load_env1(S, i, e, false);
             step_env1<false, true>(P, S, e, clipped, i, out, tally, nullptr);
-            store_env1(P, S, i, e, false);
+            store_env1(S, i, e, false);
         }
     }
     tally_flush_warp(S.stats, tally);
@@ -269,7 +269,7 @@ rollout_n1_kernel(const DevParams P, const StatePtrs S, int num_steps, uint64_t 
             const float a = random_action(action_seed, S.gid0 + (uint64_t)i, step0 + (uint64_t)k);
             step_env1<MINSEP, false>(P, S, e, a, i, none, tally, &racc);
         }
-        store_env1(P, S, i, e, MINSEP);
+        store_env1(S, i, e, MINSEP);
         if (reward_sum) reward_sum[i] += racc;
     }
     tally_flush_warp(S.stats, tally);
@@ -302,11 +302,10 @@ step_loop_kernel(const DevParams P, const StatePtrs S, const float *__restrict__
 //   6. the observation tile is written back row by row, fully coalesced.
 constexpr int kTiledWarps = 4;
 
-// Shared-memory geometry of one warp: traffic tile of E rows x TS float4 (two float4 per 32-byte
-// intruder record; TS = 2N + 1 for G == 1 so that the 16-byte reads of a quarter warp, one row per
-// lane, fall in distinct banks; TS = 2N otherwise, where a rotated start spreads them), then E
-// unpadded observation rows.
-__host__ __device__ inline int tiled_row_stride(int N, int G) { return G == 1 ? 2 * N + 1 : 2 * N; }   // float4 words
+// Shared-memory geometry of one warp: traffic tile of E rows x TS float4 (TS = N + 1 for G == 1 so
+// that the 16-byte reads of a quarter warp, one row per lane, fall in distinct banks; TS = N
+// otherwise, where a rotated start does the same job), then E unpadded observation rows.
+__host__ __device__ inline int tiled_row_stride(int N, int G) { return G == 1 ? N + 1 : N; }
 
 inline size_t tiled_warp_bytes(int N, int G)
 {
@@ -347,11 +346,11 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
 
         // 1. stage the traffic tile: contiguous in HBM, 16-byte cp.async, fully coalesced
         {
-            const Float4 *src = S.thot + env0 * N * 2;
-            const int total = nvalid * N * 2;
+            const Float4 *src = S.thot + env0 * N;
+            const int total = nvalid * N;
             for (int idx = lane; idx < total; idx += 32) {
                 int dst = idx;
-                if (G == 1) dst += (int)__umulhi((unsigned)idx, magic_n);        // + row (row padding); magic = 2^32 / 2N
+                if (G == 1) dst += (int)__umulhi((unsigned)idx, magic_n);        // + row (row padding)
                 __pipeline_memcpy_async(tile + dst, src + idx, 16);
             }
             __pipeline_commit();
@@ -386,11 +385,9 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         const bool any_residual = __any_sync(kFull, residual);      // injected float64 states only: keep it a branch
 #pragma unroll 2
         for (int m = 0; m < per_lane; ++m) {
-            const Float4 h = trow[2 * j];
-            const Vec2d vel = *(const Vec2d *)(trow + 2 * j + 1);
+            const Float4 h = trow[j];
             TrafficRec tr;
             tr.x0 = (double)h.x; tr.y0 = (double)h.y; tr.psi = (double)h.z; tr.v = (double)h.w;
-            tr.dx = vel.x; tr.dy = vel.y; tr.has_vel = true;
             if (any_residual) {
                 if (residual) {
                     const Residual r = S.tres[env * N + j];
@@ -474,8 +471,8 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
                 minsep = INFINITY;
                 j = j0;
                 for (int m = 0; m < per_lane; ++m) {
-                    TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
-                    traffic_store(P, S, env * N + j, tr, false);
+                    const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
+                    traffic_store(S, env * N + j, tr, false);
                     const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
                     minsep = fminf(minsep, en.d);
                     orow[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
@@ -537,7 +534,7 @@ int launch_tiled(const DevParams &P, const StatePtrs &S, const float *actions, c
 {
     constexpr int E = 32 / G;
     const size_t smem = tiled_smem_bytes(P.n_traffic, G);
-    const uint32_t magic_n = (uint32_t)((0x100000000ULL + 2ull * P.n_traffic - 1) / (2ull * P.n_traffic));   // idx / 2N for idx < 2^16
+    const uint32_t magic_n = (uint32_t)((0x100000000ULL + (uint64_t)P.n_traffic - 1) / (uint64_t)P.n_traffic);   // idx / N for idx < 2^16
     const int64_t warps = (S.B + E - 1) / E;
     const unsigned grid = (unsigned)((warps + kTiledWarps - 1) / kTiledWarps);
     cudaError_t err;
@@ -652,7 +649,7 @@ int acas2d_reset(const acas2d_params *params, const acas2d_state *state, const u
     if (int e = check_args(params, state)) return e;
     if (state->num_envs == 0) return 0;
     reset_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
-        make_dev_params(*params), make_state_ptrs(*state, params->n_traffic), mask, obs);
+        make_dev_params(*params), make_state_ptrs(*state), mask, obs);
     return finish_launch();
 }
 
@@ -663,7 +660,7 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
     if (state->num_envs == 0) return 0;
     if (!actions || !obs || !reward || !done) return ACAS2D_E_NULL;
     const DevParams P = make_dev_params(*params);
-    const StatePtrs S = make_state_ptrs(*state, params->n_traffic);
+    const StatePtrs S = make_state_ptrs(*state);
     const Sinks out = make_sinks(obs, reward, done, aux);
     const unsigned grid = grid_for(state->num_envs);
     cudaStream_t st = (cudaStream_t)stream;
@@ -765,7 +762,7 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
         sub.num_envs = n;
         sub.ppos = (char *)state->ppos + 16 * off;
         sub.paux = (char *)state->paux + 16 * off;
-        sub.thot = (char *)state->thot + 4 * ACAS2D_TRAFFIC_RECORD_FLOATS(N) * (int64_t)N * off;
+        sub.thot = (char *)state->thot + 16 * N * off;
         sub.tres = (char *)state->tres + 32 * N * off;
         sub.episode_idx = state->episode_idx + off;
         sub.min_sep = state->min_sep ? state->min_sep + off : nullptr;
@@ -801,7 +798,7 @@ int acas2d_inject_state(const acas2d_params *params, const acas2d_state *state, 
     if (state->num_envs == 0) return 0;
     if (!player || !traffic || !steps || !total_reward) return ACAS2D_E_NULL;
     inject_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
-        make_dev_params(*params), make_state_ptrs(*state, params->n_traffic), player, traffic, steps, total_reward);
+        make_dev_params(*params), make_state_ptrs(*state), player, traffic, steps, total_reward);
     return finish_launch();
 }
 
@@ -811,7 +808,7 @@ int acas2d_extract_state(const acas2d_params *params, const acas2d_state *state,
     if (int e = check_args(params, state)) return e;
     if (state->num_envs == 0) return 0;
     extract_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
-        make_dev_params(*params), make_state_ptrs(*state, params->n_traffic), player, traffic, steps, total_reward);
+        make_dev_params(*params), make_state_ptrs(*state), player, traffic, steps, total_reward);
     return finish_launch();
 }
 
@@ -821,7 +818,7 @@ int acas2d_observe(const acas2d_params *params, const acas2d_state *state, float
     if (state->num_envs == 0) return 0;
     if (!obs) return ACAS2D_E_NULL;
     observe_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
-        make_dev_params(*params), make_state_ptrs(*state, params->n_traffic), obs);
+        make_dev_params(*params), make_state_ptrs(*state), obs);
     return finish_launch();
 }
 
@@ -833,7 +830,7 @@ int acas2d_rollout_random(const acas2d_params *params, const acas2d_state *state
     if (state->num_envs == 0 || num_steps <= 0) return 0;
     DevParams P = make_dev_params(*params);
     P.auto_reset = 1;
-    const StatePtrs S = make_state_ptrs(*state, 1);
+    const StatePtrs S = make_state_ptrs(*state);
     const unsigned grid = grid_for(state->num_envs);
     if (S.min_sep) rollout_n1_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(P, S, num_steps, action_seed, step0, reward_sum);
     else rollout_n1_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(P, S, num_steps, action_seed, step0, reward_sum);
@@ -850,7 +847,7 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
     if (state->num_envs == 0) return 0;
     if (!weights || !obs_in || !obs_out || !reward || !done) return ACAS2D_E_NULL;
     const DevParams P = make_dev_params(*params);
-    const StatePtrs S = make_state_ptrs(*state, params->n_traffic);
+    const StatePtrs S = make_state_ptrs(*state);
     const Sinks out = make_sinks(obs_out, reward, done, aux);
     static int sms = 0;
     if (sms == 0) {

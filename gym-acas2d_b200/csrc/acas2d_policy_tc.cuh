@@ -266,7 +266,7 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             e.minsep = 0.0f;
             e.respawned = false;
             step_env1<false, true>(P, S, e, clipped, i, out, tally, nullptr);
-            store_env1(P, S, i, e, false);
+            store_env1(S, i, e, false);
         }
         base = next_base;
         have = have_next;

@@ -68,7 +68,7 @@ class BatchedACAS2D:
             # ---- state (layout: include/acas2d_b200.h)
             self.ppos = torch.zeros(B, 2, dtype=f64, device=dev)
             self.paux = torch.zeros(B, 2, dtype=f64, device=dev)          # 16 B records {psi, steps, ep_return}
-            self.thot = torch.zeros(B, N, 4 if N == 1 else 8, dtype=f32, device=dev)   # hot intruder records (acas2d_b200.h)
+            self.thot = torch.zeros(B, N, 4, dtype=f32, device=dev)          # {x0, y0, psi, v}: all a step reads
             self.tres = torch.zeros(B, N, 4, dtype=f64, device=dev)          # cold float64 remainders (injected states)
             self.episode_idx = torch.zeros(B, dtype=torch.int32, device=dev)
             self.min_sep = torch.zeros(B, dtype=f32, device=dev) if track_min_sep else None

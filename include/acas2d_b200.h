@@ -26,15 +26,11 @@
  *                               psi in degrees (aircraft.py:12); steps == game.steps
  *                               (game.py:30,197) | ACAS2D_STEPS_RESIDUAL_BIT; ep_return ==
  *                               game.total_reward so far (game.py:32,287)
- *   thot        float[B][N][R]  intruder record, R = ACAS2D_TRAFFIC_RECORD_FLOATS(N):
- *                               R = 4 (N == 1): {x0, y0, psi, v} -- position at steps == 1, heading [deg], speed;
- *                               R = 8 (N > 1):  the same four floats followed by two float64 {dx, dy} =
- *                               v*dt*(cos psi, sin psi), the displacement per step (cached so that a step does
- *                               not redo one sin/cos per intruder).
- *                               The intruder flies a straight line (game.py:243-245, a_lat is always 0):
- *                               position after k moves = (x0, y0) + k * (dx, dy), evaluated in float64.
- *                               Spawned intruders are float32-representable by construction, so the record
- *                               is exact and is all a step reads.
+ *   thot        float[B][N][4]  intruder record {x0, y0, psi, v}: position at steps == 1, heading [deg],
+ *                               speed.  The intruder flies a straight line (game.py:243-245, a_lat is
+ *                               always 0): position after k moves = (x0, y0) + k * v*dt*(cos psi, sin psi),
+ *                               evaluated in float64.  Spawned intruders are float32-representable by
+ *                               construction, so this 16-byte record is exact and is all a step reads.
  *   tres        double[B][N][4] full - float32(full) of the same four values.  Cold: written by
  *                               acas2d_inject_state, read by step / extract only for envs whose
  *                               paux.steps carries ACAS2D_STEPS_RESIDUAL_BIT (injected float64 states).
@@ -59,9 +55,6 @@ extern "C" {
 #define ACAS2D_E_NO_DEVICE   (-4)  /* no CUDA device / not an sm_100 device */
 
 #define ACAS2D_MAX_TRAFFIC 1024
-
-/* floats per intruder record in `thot` */
-#define ACAS2D_TRAFFIC_RECORD_FLOATS(n_traffic) ((n_traffic) == 1 ? 4 : 8)
 
 /* bit of paux.steps: this env's intruder records need their float64 residuals (tres) */
 #define ACAS2D_STEPS_RESIDUAL_BIT 0x40000000

@@ -52,7 +52,7 @@ class HostBatch:
         self.variant = (0 if N == 1 else 1) if variant is None else variant
         f8, f4 = np.float64, np.float32
         self.ppos = np.zeros((B, 2), f8); self.paux = np.zeros((B, 2), f8)
-        self.thot = np.zeros((B, N, 4 if N == 1 else 8), f4); self.tres = np.zeros((B, N, 4), f8)
+        self.thot = np.zeros((B, N, 4), f4); self.tres = np.zeros((B, N, 4), f8)
         self.episode_idx = np.zeros(B, np.uint32)
         self.min_sep = np.zeros(B, f4) if track_min_sep else None
         self.stats = np.zeros((_native.STAT_SLOTS, _native.STAT_FIELDS), np.int64)

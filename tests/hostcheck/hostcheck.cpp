@@ -41,7 +41,7 @@ extern "C" {
 int hostcheck_reset(const acas2d_params *p, const acas2d_state *s, const uint8_t *mask, float *obs)
 {
     const DevParams P = make_dev_params(*p);
-    const StatePtrs S = make_state_ptrs(*s, p->n_traffic);
+    const StatePtrs S = make_state_ptrs(*s);
     for (int64_t i = 0; i < S.B; ++i)
         if (!mask || mask[i]) reset_env(P, S, i, obs);
     return 0;
@@ -52,7 +52,7 @@ int hostcheck_step(const acas2d_params *p, const acas2d_state *s, const float *a
                    float *reward, uint8_t *done, const acas2d_step_aux *aux, int variant)
 {
     const DevParams P = make_dev_params(*p);
-    const StatePtrs S = make_state_ptrs(*s, p->n_traffic);
+    const StatePtrs S = make_state_ptrs(*s);
     const Sinks out = sinks_of(obs, reward, done, aux);
     Tally tally;
     tally_clear(tally);
@@ -63,11 +63,11 @@ int hostcheck_step(const acas2d_params *p, const acas2d_state *s, const float *a
             if (S.min_sep) {
                 load_env1(S, i, e, true);
                 step_env1<true, true>(P, S, e, actions[i], i, out, tally, nullptr);
-                store_env1(P, S, i, e, true);
+                store_env1(S, i, e, true);
             } else {
                 load_env1(S, i, e, false);
                 step_env1<false, true>(P, S, e, actions[i], i, out, tally, nullptr);
-                store_env1(P, S, i, e, false);
+                store_env1(S, i, e, false);
             }
         } else {
             if (S.min_sep) step_env_loop<true>(P, S, i, actions[i], out, tally);
@@ -83,7 +83,7 @@ int hostcheck_rollout_random(const acas2d_params *p, const acas2d_state *s, int3
 {
     DevParams P = make_dev_params(*p);
     P.auto_reset = 1;
-    const StatePtrs S = make_state_ptrs(*s, p->n_traffic);
+    const StatePtrs S = make_state_ptrs(*s);
     Tally tally;
     tally_clear(tally);
     Sinks none = {};
@@ -96,7 +96,7 @@ int hostcheck_rollout_random(const acas2d_params *p, const acas2d_state *s, int3
             if (S.min_sep) step_env1<true, false>(P, S, e, a, i, none, tally, &racc);
             else step_env1<false, false>(P, S, e, a, i, none, tally, &racc);
         }
-        store_env1(P, S, i, e, S.min_sep != nullptr);
+        store_env1(S, i, e, S.min_sep != nullptr);
         if (reward_sum) reward_sum[i] += racc;
     }
     flush(S, tally);
@@ -113,7 +113,7 @@ int hostcheck_random_actions(const acas2d_state *s, uint64_t action_seed, uint64
 int hostcheck_observe(const acas2d_params *p, const acas2d_state *s, float *obs)
 {
     const DevParams P = make_dev_params(*p);
-    const StatePtrs S = make_state_ptrs(*s, p->n_traffic);
+    const StatePtrs S = make_state_ptrs(*s);
     for (int64_t i = 0; i < S.B; ++i) observe_env(P, S, i, obs);
     return 0;
 }
@@ -122,7 +122,7 @@ int hostcheck_inject(const acas2d_params *p, const acas2d_state *s, const double
                      const int32_t *steps, const double *total_reward)
 {
     const DevParams P = make_dev_params(*p);
-    const StatePtrs S = make_state_ptrs(*s, p->n_traffic);
+    const StatePtrs S = make_state_ptrs(*s);
     for (int64_t i = 0; i < S.B; ++i) inject_env(P, S, i, player, traffic, steps, total_reward);
     return 0;
 }
@@ -131,7 +131,7 @@ int hostcheck_extract(const acas2d_params *p, const acas2d_state *s, double *pla
                       int32_t *steps, double *total_reward)
 {
     const DevParams P = make_dev_params(*p);
-    const StatePtrs S = make_state_ptrs(*s, p->n_traffic);
+    const StatePtrs S = make_state_ptrs(*s);
     for (int64_t i = 0; i < S.B; ++i) extract_env(P, S, i, player, traffic, steps, total_reward);
     return 0;
 }
