@@ -14,6 +14,9 @@
 #ifndef ACAS2D_OUT_STORE
 #define ACAS2D_OUT_STORE 1      /* outputs are not re-read by the step: streaming */
 #endif
+#ifndef ACAS2D_STORE_256
+#define ACAS2D_STORE_256 0      /* experiment: 256-bit st.global.v8.f32 for the 32-byte observation row */
+#endif
 #ifndef ACAS2D_STATE_STORE
 #define ACAS2D_STATE_STORE 1    /* measured: 95.3 -> 91.6 us at 4 Mi envs (state does not fit L2; evict-first keeps the
                                    next step's inputs from being pushed out by lines nobody re-reads soon) */
@@ -228,8 +231,14 @@ ACAS_HD void store_obs8(float *row, const PlayerView &v, const Encounter &e, con
 {
     Float4 a; a.x = v.obs[0]; a.y = v.obs[1]; a.z = v.obs[2]; a.w = v.obs[3];
     Float4 b; b.x = v.obs[4]; b.y = e.d * P.inv_d_sep_max; b.z = e.d_cpa * P.inv_d_cpa_max; b.w = e.v_c * P.vc_scale;
+#if defined(__CUDA_ARCH__) && ACAS2D_STORE_256
+    // one 256-bit streaming store per row (sm_100): a full 32-byte sector per thread in one request
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(row), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
     ACAS_STCS((Float4 *)row, a);
     ACAS_STCS((Float4 *)row + 1, b);
+#endif
 }
 
 // One environment step for a single-intruder env held in registers.
