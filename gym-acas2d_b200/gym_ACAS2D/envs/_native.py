@@ -105,6 +105,11 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            try:                                        # build on demand (nvcc, sm_100a); still no CPU fallback
+                build()
+            except Exception:                           # noqa: BLE001
+                pass
+        if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  The ACAS-2D batched step has no CPU fallback.")
