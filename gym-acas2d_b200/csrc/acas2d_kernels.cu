@@ -460,7 +460,42 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
                 }
                 __syncwarp();
             }
-            if (respawn) {
+            if (G < 32) {
+                // A respawn is ~230 instructions per intruder; with G lanes per env a lone respawning env
+                // would run it at G/32 utilisation (1/32 in thread-per-env mode).  All 32 lanes take the intruders of each respawning
+                // env of the warp in turn instead (warp-uniform loop over the rows).
+                for (int row = 0; row < nvalid; ++row) {
+                    if (!((respawn_mask >> (row * G)) & 1u)) continue;
+                    const int64_t renv = env0 + row;
+                    uint32_t episode = 0;
+                    if (lane == 0) { episode = S.episode_idx[renv]; S.episode_idx[renv] = episode + 1u; }
+                    episode = __shfl_sync(kFull, episode, 0);
+                    const uint64_t gid = S.gid0 + (uint64_t)renv;
+                    const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
+                    Player rp;
+                    rp.x = P.player_x0; rp.y = P.player_y0;
+                    player_set_heading(P, rp, sp.player_psi, 0.0);
+                    float ms = INFINITY;
+                    float *rrow = otile + row * L;
+                    for (int jj = lane; jj < N; jj += 32) {
+                        const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, jj, sp);
+                        traffic_store(S, renv * N + jj, tr, false);
+                        const Encounter en = encounter(P, rp, intruder_at(P, tr, 0.0));
+                        ms = fminf(ms, en.d);
+                        rrow[5 + 3 * jj + 0] = en.d * P.inv_d_sep_max;
+                        rrow[5 + 3 * jj + 1] = en.d_cpa * P.inv_d_cpa_max;
+                        rrow[5 + 3 * jj + 2] = en.v_c * P.vc_scale;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ms = fminf(ms, __shfl_xor_sync(kFull, ms, o));
+                    if (lane == 0) {
+                        const PlayerView v1 = player_view(P, rp, 1);
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) rrow[q] = v1.obs[q];
+                    }
+                    if (e == row) { p = rp; minsep = ms; steps_out = 1; ret = 0.0f; }
+                }
+            } else if (respawn) {
                 uint32_t episode = 0;
                 if (sub == 0) { episode = S.episode_idx[env]; S.episode_idx[env] = episode + 1u; }
                 episode = __shfl_sync(__activemask(), episode, e * G);
