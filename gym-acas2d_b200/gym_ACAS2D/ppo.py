@@ -191,6 +191,26 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
     return history
 
 
+def evaluate(actor: MlpActor, episodes: int = 4096, device="cuda", seed: int = 99, tensor_cores: bool = False) -> Dict[str, float]:
+    """Deterministic evaluation, ``testing_main.py:62-108`` style (``model.predict(obs, deterministic=True)``):
+    the first episode of ``episodes`` envs, statistics as in the reference's notebooks."""
+    dev = torch.device(device)
+    env = BatchedACAS2D(episodes, device=dev, seed=seed, auto_reset=True)
+    env.reset()
+    finished = torch.zeros(episodes, dtype=torch.bool, device=dev)
+    outcome = torch.zeros(episodes, dtype=torch.uint8, device=dev)
+    length = torch.zeros(episodes, dtype=torch.int32, device=dev)
+    ret = torch.zeros(episodes, device=dev)
+    for _ in range(int(env.params.max_steps) + 1):
+        _, _, d = env.policy_step(actor, deterministic=True, tensor_cores=tensor_cores)
+        new = d & ~finished
+        outcome[new] = env.outcome[new]; length[new] = env.ep_length[new]; ret[new] = env.ep_return[new]
+        finished |= new
+    return dict(episodes=episodes, goal_rate=float((outcome == 1).float().mean()),
+                collision_rate=float((outcome == 2).float().mean()), timeout_rate=float((outcome == 3).float().mean()),
+                mean_steps=float(length.float().mean()), mean_return=float(ret.mean()), std_return=float(ret.std()))
+
+
 if __name__ == "__main__":
     import argparse
     import json
@@ -203,5 +223,15 @@ if __name__ == "__main__":
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     hist = train(a.envs, a.n_steps, a.iterations, minibatches=a.minibatches, tensor_cores=not a.fp32)
+    import os
+    result = {"training": hist}
+    trained = MlpActor(train.last_policy.sb3_state_dict(), "cuda")
+    result["eval_trained_here"] = evaluate(trained)
+    print("deterministic eval, policy trained here:      ", result["eval_trained_here"])
+    fixture = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                           "tests", "golden", "ppo_policy_1048576_11.npz")
+    if os.path.exists(fixture):
+        result["eval_reference_agent"] = evaluate(MlpActor.from_file(fixture, "cuda"))
+        print("deterministic eval, the reference's saved agent:", result["eval_reference_agent"])
     if a.out:
-        json.dump(hist, open(a.out, "w"), indent=1)
+        json.dump(result, open(a.out, "w"), indent=1)
