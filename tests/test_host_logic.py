@@ -106,6 +106,53 @@ def test_stats_allreduce_world_size_2_gloo(tmp_path):
     assert out.stdout.count("ok") == 2
 
 
+def test_sharded_rollout_world_size_2_gloo(tmp_path):
+    """The multi-GPU path on CPU: two gloo ranks each own a contiguous block of global env ids (here
+    stepped by the g++ host build of the device source), exchange nothing per step, and all-reduce the
+    seven episode counters at the end.  The result must equal the single-process run of the whole batch:
+    spawns, action streams and statistics depend on the global env id only."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, numpy as np, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'gym-acas2d_b200')!r})
+        from tests.hostcheck import HostBatch
+        from gym_ACAS2D.envs.stats import reduce_counters, summarise
+        import bench
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        TOTAL, T = 600, 260
+        off, n = bench.shard(TOTAL, world, rank)
+        mine = HostBatch(n, 1, seed=13, env_id_offset=off, auto_reset=True)
+        mine.reset()
+        ex = mine.extract_state(); ex["steps"][:] = 800 + (np.arange(off, off + n) % 190)      # plenty of episode ends
+        mine.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+        for t in range(T):
+            mine.step(mine.random_actions(t, action_seed=5))
+        total = reduce_counters(torch.from_numpy(mine.episode_counters().copy()))
+        if rank == 0:
+            full = HostBatch(TOTAL, 1, seed=13, env_id_offset=0, auto_reset=True)
+            full.reset()
+            ex = full.extract_state(); ex["steps"][:] = 800 + (np.arange(TOTAL) % 190)
+            full.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+            for t in range(T):
+                full.step(full.random_actions(t, action_seed=5))
+            assert np.array_equal(full.episode_counters(), total.numpy()), (full.episode_counters(), total)
+            assert np.array_equal(full.ppos[:n], mine.ppos) and np.array_equal(full.obs[:n], mine.obs)
+            s = summarise(torch.from_numpy(mine.episode_counters().copy()), reduce=True)
+            assert s["episodes"] == int(total[0]) and s["episodes"] >= TOTAL // 2
+        else:
+            summarise(torch.from_numpy(mine.episode_counters().copy()), reduce=True)
+        dist.destroy_process_group()
+        print("ok", rank)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
+
+
 def test_bench_sharding_arithmetic():
     """Contiguous global env ids per rank: union of shards == the whole batch."""
     sys.path.insert(0, ROOT)
