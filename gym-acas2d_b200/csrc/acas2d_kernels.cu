@@ -169,9 +169,11 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         e.steps = pa.steps & kStepsMask;
         e.residual = (pa.steps & kResidualBit) != 0;
         e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
-        if (__builtin_expect(e.residual, 0)) {
-            const Residual r = S.tres[i];
-            e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
+        if (__any_sync(kFull, e.residual)) {               // injected float64 states only: a real (warp-uniform) branch
+            if (e.residual) {
+                const Residual r = S.tres[i];
+                e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
+            }
         }
         e.minsep = 0.0f;
         e.respawned = false;
