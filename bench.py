@@ -355,6 +355,20 @@ def run_ours(args):
         other["policy_rollout_tcgen05_mlp_env_step"] = {
             "value": world * B * 4 * pol_steps / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / (4 * pol_steps),
             "note": "same, hidden layers as tcgen05.mma kind::tf32 with TMEM accumulators (128 envs per CTA tile)"}
+        # the SB3-style numpy VecEnv surface (host arrays in / out, per-env info dicts) at 4096 envs
+        from gym_ACAS2D.envs import ACAS2DVecEnv
+        import numpy as np
+        venv = ACAS2DVecEnv(4096, device=dev, seed=13)
+        venv.reset()
+        va = np.zeros((4096, 1), np.float32)
+        for _ in range(5):
+            venv.step(va)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            venv.step(va)
+        dt = time.perf_counter() - t0
+        other["vecenv_numpy_surface_4096_envs"] = {"value": world * 4096 * 200 / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / 200,
+                                                   "note": "ACAS2DVecEnv.step(np actions) -> np obs / rewards / dones + list of info dicts; wall clock"}
         small = BatchedACAS2D(4096, n_traffic=1, device=dev, seed=13, env_id_offset=0, auto_reset=True)
         small.reset()
         sgraph = small.capture_steps(actions[:, :4096].contiguous(), num_steps=200)      # 200 steps per replay
