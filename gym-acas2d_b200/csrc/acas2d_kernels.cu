@@ -621,6 +621,39 @@ observe_kernel(const DevParams P, const StatePtrs S, float *__restrict__ obs)
     if (i < S.B) observe_env(P, S, i, obs);
 }
 
+// Off-path debug view of ONE env: the scene of game.view() (game.py:323-347) without sprites
+// and HUD text -- sky background, discs of AIRCRAFT_SIZE for player (black, with a heading tick), goal
+// (green) and intruders (grey), 1-px circles of COLLISION_RADIUS (red) and GOAL_RADIUS (yellow).
+__global__ void __launch_bounds__(kBlock)
+render_kernel(const DevParams P, const StatePtrs S, const int64_t env, const int W, const int H,
+              const float aircraft_r, const float collision_r, const float goal_r, uint8_t *__restrict__ rgb)
+{
+    const int64_t pix = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (pix >= (int64_t)W * H) return;
+    const float x = (float)(pix % W) + 0.5f, y = (float)(pix / W) + 0.5f;
+    uint8_t r = 60, g = 150, b = 220;                                         // SKY_RGB
+    const Vec2d pp = S.ppos[env];
+    const PlayerAux pa = S.paux[env];
+    const int st = pa.steps & kStepsMask;
+    auto ring = [&](float cx, float cy, float rad) { return fabsf(sqrtf((x - cx) * (x - cx) + (y - cy) * (y - cy)) - rad) < 0.75f; };
+    auto disc = [&](float cx, float cy, float rad) { return (x - cx) * (x - cx) + (y - cy) * (y - cy) < rad * rad; };
+    const float gx = (float)P.goal_x, gy = (float)P.goal_y, px = (float)pp.x, py = (float)pp.y;
+    if (disc(gx, gy, aircraft_r)) { r = 0; g = 255; b = 0; }
+    for (int j = 0; j < P.n_traffic; ++j) {
+        const TrafficRec tr = traffic_load(S, env * P.n_traffic + j, (pa.steps & kResidualBit) != 0);
+        const Intruder t = intruder_at(P, tr, (double)(st - 1));
+        if (disc((float)t.x, (float)t.y, aircraft_r)) { r = 90; g = 90; b = 90; }
+        if (ring((float)t.x, (float)t.y, collision_r)) { r = 255; g = 0; b = 0; }
+    }
+    double s, c;
+    sincos_deg(pa.psi, &s, &c);
+    const float tx = x - px, ty = y - py, along = tx * (float)c + ty * (float)s, across = -tx * (float)s + ty * (float)c;
+    if (disc(px, py, aircraft_r) || (along > 0.0f && along < 2.5f * aircraft_r && fabsf(across) < 1.5f)) { r = 0; g = 0; b = 0; }
+    if (ring(px, py, collision_r)) { r = 255; g = 0; b = 0; }
+    if (ring(gx, gy, goal_r)) { r = 255; g = 255; b = 0; }
+    rgb[3 * pix + 0] = r; rgb[3 * pix + 1] = g; rgb[3 * pix + 2] = b;
+}
+
 __global__ void __launch_bounds__(kBlock)
 random_actions_kernel(int64_t B, uint64_t gid0, uint64_t action_seed, uint64_t step_index, float *__restrict__ actions)
 {
@@ -856,6 +889,18 @@ int acas2d_observe(const acas2d_params *params, const acas2d_state *state, float
     if (!obs) return ACAS2D_E_NULL;
     observe_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
         make_dev_params(*params), make_state_ptrs(*state), obs);
+    return finish_launch();
+}
+
+int acas2d_render(const acas2d_params *params, const acas2d_state *state, int64_t env_index, uint8_t *rgb, void *stream)
+{
+    if (int e = check_args(params, state)) return e;
+    if (!rgb) return ACAS2D_E_NULL;
+    if (env_index < 0 || env_index >= state->num_envs) return ACAS2D_E_BAD_SIZE;
+    const int W = (int)params->width, H = (int)params->height;
+    render_kernel<<<grid_for((int64_t)W * H), kBlock, 0, (cudaStream_t)stream>>>(
+        make_dev_params(*params), make_state_ptrs(*state), env_index, W, H, (float)(params->aircraft_size / 2),
+        (float)params->collision_radius, (float)params->goal_radius, rgb);
     return finish_launch();
 }
 

@@ -32,7 +32,7 @@ POLICY_FLOATS = 4804
 
 EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
-           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe")
+           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -91,6 +91,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_rollout_random.argtypes = [PP, SP, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
     lib.acas2d_random_actions.argtypes = [SP, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
     lib.acas2d_observe.argtypes = [PP, SP, vp, vp]
+    lib.acas2d_render.argtypes = [PP, SP, ctypes.c_int64, vp, vp]
     lib.acas2d_launch_count.argtypes = []
     lib.acas2d_launch_count.restype = ctypes.c_int64
     lib.acas2d_set_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]

@@ -310,6 +310,17 @@ class BatchedACAS2D:
         self.launches += 1
         return self.obs
 
+    def render(self, env_index: int = 0) -> torch.Tensor:
+        """Debug frame of one env: uint8 [HEIGHT, WIDTH, 3] device tensor (the scene of the reference's
+        ``game.view()`` without sprites / HUD text).  Off the hot path."""
+        H, W = int(self.params.height), int(self.params.width)
+        img = torch.empty(H, W, 3, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_render(self._p(), self._s(), int(env_index), img.data_ptr(), self._stream()),
+                          "acas2d_render")
+        self.launches += 1
+        return img
+
     def extract_state(self) -> Dict[str, np.ndarray]:
         """Current games as numpy float64: player [B,3], traffic [B,N,4], steps, total_reward, episode_idx."""
         B, N, dev = self.num_envs, self.n_traffic, self.device

@@ -28,7 +28,7 @@ else:
 
 
 class ACAS2DEnv(_EnvBase):
-    metadata = {"render.modes": ["human"]}
+    metadata = {"render.modes": ["human", "rgb_array"]}
 
     def __init__(self, n_traffic=None, device="cuda", seed=None, env_id=0, verbose=False, settings=None):
         self._core = BatchedACAS2D(1, n_traffic=n_traffic, device=device, seed=seed, env_id_offset=env_id,
@@ -65,6 +65,10 @@ class ACAS2DEnv(_EnvBase):
         return obs[0].cpu().numpy().astype(np.float64)
 
     def render(self, mode="human"):
+        """``mode="rgb_array"`` returns a uint8 [HEIGHT, WIDTH, 3] frame; ``"human"`` (the reference's pygame
+        window, game.py:316-431) is a no-op: nothing is drawn on the hot path."""
+        if mode == "rgb_array":
+            return self._core.render(0).cpu().numpy()
         return None
 
     def close(self):

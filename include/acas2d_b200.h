@@ -179,6 +179,10 @@ int acas2d_extract_state(const acas2d_params *params, const acas2d_state *state,
  * reset observation for a state injected at steps == 1).  Does not modify the state. */
 int acas2d_observe(const acas2d_params *params, const acas2d_state *state, float *obs, void *stream);
 
+/* Off-path debug frame of env `env_index`: uint8 rgb[HEIGHT][WIDTH][3] (device pointer), the scene of
+ * ACAS2DGame.view() (game.py:323-347) without sprites and HUD text.  Not part of the hot path. */
+int acas2d_render(const acas2d_params *params, const acas2d_state *state, int64_t env_index, uint8_t *rgb, void *stream);
+
 /* Synthetic benchmark path: K consecutive auto-resetting steps per launch with actions
  * drawn in-kernel, a ~ U(-1,1) from Philox(key = action_seed, counter = (global env id,
  * step0 + k)).  State stays in registers between the K steps; nothing but the state, the

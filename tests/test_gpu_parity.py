@@ -521,3 +521,24 @@ def test_golden_csv_replayed_on_the_gpu(cuda, golden_dir):
         assert list(df.columns) == records.TESTING_COLUMNS and len(df) == 3
         records.to_csv(rows[:3], os.path.join(d, "b.csv"), records.BASELINE_COLUMNS)
         assert list(pd.read_csv(os.path.join(d, "b.csv")).columns) == records.BASELINE_COLUMNS
+
+
+def test_headless_render_frame(cuda):
+    """debug frame of one env -- sky, goal disc + yellow GOAL_RADIUS ring, player disc + red
+    COLLISION_RADIUS ring, intruder disc + ring, at the positions of the device state."""
+    env = make(3, 2, auto_reset=False)
+    env.reset()
+    pl = np.array([[300.0, 400.0, 0.0]] * 3); tr = np.tile([[900.0, 700.0, 200.0, 180.0], [1200.0, 200.0, 200.0, 90.0]], (3, 1, 1))
+    env.inject_state(pl, tr)
+    img = npy(env.render(1))
+    assert img.shape == (1000, 1600, 3) and img.dtype == np.uint8
+    assert tuple(img[5, 5]) == (60, 150, 220)                       # SKY_RGB
+    assert tuple(img[400, 300]) == (0, 0, 0)                        # player
+    assert tuple(img[400, 300 + 48]) == (255, 0, 0)                 # COLLISION_RADIUS ring
+    assert tuple(img[700, 900]) == (90, 90, 90) and tuple(img[200, 1200]) == (90, 90, 90)
+    assert tuple(img[500, 1456]) == (0, 255, 0)                     # goal
+    assert tuple(img[500, 1456 - 144]) == (255, 255, 0)             # GOAL_RADIUS ring
+    import gym_ACAS2D
+    e = gym_ACAS2D.make("ACAS2D-v0")
+    frame = e.render(mode="rgb_array")
+    assert frame.shape == (1000, 1600, 3) and tuple(frame[500, 48]) == (0, 0, 0) and e.render() is None
