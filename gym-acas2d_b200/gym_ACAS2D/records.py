@@ -54,8 +54,8 @@ def record_episodes(env: BatchedACAS2D, policy: Optional[Callable[[torch.Tensor]
     obs = env.observe() if start is not None else env.obs
     st = env.extract_state()
     pl, tr = st["player"], st["traffic"]
-    path = [[(pl[b, 0], pl[b, 1])] for b in range(B)]
-    tpaths = [[[(tr[b, n, 0], tr[b, n, 1])] for n in range(N)] for b in range(B)]
+    path = [[(float(pl[b, 0]), float(pl[b, 1]))] for b in range(B)]                 # plain floats: the CSV must literal_eval
+    tpaths = [[[(float(tr[b, n, 0]), float(tr[b, n, 1]))] for n in range(N)] for b in range(B)]
     rec = {k: [[] for _ in range(B)] for k in _KEYS}
 
     def push(alive, o, psi, d_sep, a_lat, discount):
@@ -81,9 +81,9 @@ def record_episodes(env: BatchedACAS2D, policy: Optional[Callable[[torch.Tensor]
         ex = env.extract_state()
         pl, tr = ex["player"], ex["traffic"]
         for b in np.flatnonzero(alive):
-            path[b].append((pl[b, 0], pl[b, 1]))
+            path[b].append((float(pl[b, 0]), float(pl[b, 1])))
             for n in range(N):
-                tpaths[b][n].append((tr_before[b, n, 0], tr_before[b, n, 1]))        # recorded before the intruders move (Q10)
+                tpaths[b][n].append((float(tr_before[b, n, 0]), float(tr_before[b, n, 1])))   # before the intruders move (Q10)
         push(alive, obs.cpu().numpy(), pl[:, 2], sep(pl, tr_before), act.cpu().numpy().astype(np.float64) * p.acc_lat_limit,
              1 - ex["steps"] / p.max_steps)
         d_path += np.where(alive, p.airspeed / p.fps, 0.0)                           # game.py:241

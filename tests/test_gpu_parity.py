@@ -519,6 +519,9 @@ def test_golden_csv_replayed_on_the_gpu(cuda, golden_dir):
         records.to_csv(rows[:3], os.path.join(d, "t.csv"))
         df = pd.read_csv(os.path.join(d, "t.csv"))
         assert list(df.columns) == records.TESTING_COLUMNS and len(df) == 3
+        import ast
+        assert ast.literal_eval(df["Path"][0])[0] == (48.0, 500.0)                  # parses like the reference's CSV
+        assert len(ast.literal_eval(df["Traffic Paths"][0])[0]) == len(ast.literal_eval(df["Path"][0]))
         records.to_csv(rows[:3], os.path.join(d, "b.csv"), records.BASELINE_COLUMNS)
         assert list(pd.read_csv(os.path.join(d, "b.csv")).columns) == records.BASELINE_COLUMNS
 
