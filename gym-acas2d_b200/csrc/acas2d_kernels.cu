@@ -56,7 +56,8 @@ int finish_launch()
     return (int)cudaGetLastError();
 }
 
-// Tuning knobs for experiments (read once): ACAS2D_N1_OCC = 3|4 blocks/SM for the N == 1 kernel,
+// Tuning knobs for experiments (read once): ACAS2D_N1_OCC = 1..4 resident CTAs/SM for the N == 1 kernel
+// (fewer concurrent DRAM streams win: 2 CTAs x 2 stages = 87.7 us, 3 x 2 = 91.3, 4 x 2 = 93.0, 1 x 2 = 118),
 // ACAS2D_FORCE_LOOP = 1 routes N > 1 to the simple per-thread kernel the tiled one is checked against.
 struct Tuning { int n1_occupancy; bool force_loop; int n1_tma; int n1_stages; };
 Tuning &tuning()
@@ -64,7 +65,7 @@ Tuning &tuning()
     static Tuning t = [] {
         Tuning x;
         const char *o = std::getenv("ACAS2D_N1_OCC");
-        x.n1_occupancy = (o && std::atoi(o) == 4) ? 4 : 3;      // measured best: 3 CTAs/SM, 80 regs, no spills
+        x.n1_occupancy = (o && std::atoi(o) >= 1 && std::atoi(o) <= 4) ? std::atoi(o) : 2;   // measured best: 2 CTAs/SM
         const char *f = std::getenv("ACAS2D_FORCE_LOOP");
         x.force_loop = f && std::atoi(f) != 0;
         const char *t = std::getenv("ACAS2D_N1_TMA");
@@ -102,16 +103,17 @@ step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ a
 // expect_tx), the CTA is persistent (grid = SMs x resident CTAs) and walks tiles round-robin; all
 // 256 threads only compute out of shared memory and stream their results straight from registers
 // (128-bit streaming stores).  Bytes in flight per SM = OCC x STAGES x 13 KB, independent of how
-// many warps are stalled on arithmetic.
-constexpr int kTileEnvs = kBlock;
-constexpr int kStageBytes = kTileEnvs * (16 + 16 + 16 + 4);          // ppos | paux | thot | action
-constexpr int kOffPaux = kTileEnvs * 16, kOffThot = kTileEnvs * 32, kOffAct = kTileEnvs * 48;
+// many warps are stalled on arithmetic; the best setting is the one with the FEWEST concurrent
+// streams that still keeps the schedulers fed (2 CTAs/SM x 2 stages).
+// TILE = envs per tile = threads per CTA (256 or 512); a stage holds ppos | paux | thot | action.
 
-template <int STAGES, int OCC>
-__global__ void __launch_bounds__(kBlock, OCC)
+template <int STAGES, int OCC, int TILE>
+__global__ void __launch_bounds__(TILE, OCC)
 step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
                    const long long full_tiles)
 {
+    constexpr int kTileEnvs = TILE, kStageBytes = TILE * (16 + 16 + 16 + 4);
+    constexpr int kOffPaux = TILE * 16, kOffThot = TILE * 32, kOffAct = TILE * 48;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
     const int tid = threadIdx.x;
@@ -195,16 +197,17 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
     tally_flush_warp(S.stats, tally);
 }
 
-template <int STAGES, int OCC>
+template <int STAGES, int OCC, int TILE = 256>
 int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
 {
+    constexpr int kTileEnvs = TILE, kStageBytes = TILE * (16 + 16 + 16 + 4);
     static int sms = 0;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (!attr_set[dev & 63]) {                      // function attributes are per device
-        cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              STAGES * kStageBytes + 64);
         attr_set[dev & 63] = true;
     }
@@ -212,7 +215,7 @@ int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, 
     long long grid = (long long)sms * OCC;
     const long long tiles = full_tiles + ((S.B % kTileEnvs) ? 1 : 0);
     if (grid > tiles) grid = tiles;
-    step_n1_tma_kernel<STAGES, OCC><<<(unsigned)grid, kBlock, STAGES * kStageBytes + 64, st>>>(P, S, actions, out, full_tiles);
+    step_n1_tma_kernel<STAGES, OCC, TILE><<<(unsigned)grid, TILE, STAGES * kStageBytes + 64, st>>>(P, S, actions, out, full_tiles);
     return 0;
 }
 
@@ -739,10 +742,19 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
         const bool aligned = (((uintptr_t)actions | (uintptr_t)S.ppos | (uintptr_t)S.paux | (uintptr_t)S.thot) & 15) == 0;
         if (!S.min_sep && tuning().n1_tma && aligned) {
             const int stages = tuning().n1_stages;
-            if (occ4) {
+            const int occ = tuning().n1_occupancy;
+            if (occ == 4) {
                 if (stages <= 2) launch_n1_tma<2, 4>(P, S, actions, out, st);
                 else if (stages == 3) launch_n1_tma<3, 4>(P, S, actions, out, st);
                 else launch_n1_tma<4, 4>(P, S, actions, out, st);
+            } else if (occ == 2) {
+                if (stages <= 2) launch_n1_tma<2, 2>(P, S, actions, out, st);
+                else if (stages == 3) launch_n1_tma<3, 2>(P, S, actions, out, st);
+                else launch_n1_tma<4, 2>(P, S, actions, out, st);
+            } else if (occ == 1) {
+                if (stages <= 2) launch_n1_tma<2, 1>(P, S, actions, out, st);
+                else if (stages == 3) launch_n1_tma<3, 1>(P, S, actions, out, st);
+                else launch_n1_tma<4, 1>(P, S, actions, out, st);
             } else {
                 if (stages <= 2) launch_n1_tma<2, 3>(P, S, actions, out, st);
                 else if (stages == 3) launch_n1_tma<3, 3>(P, S, actions, out, st);
@@ -983,7 +995,7 @@ int64_t acas2d_launch_count(void) { return g_launches.load(std::memory_order_rel
 
 int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop)
 {
-    if (n1_occupancy == 3 || n1_occupancy == 4) tuning().n1_occupancy = n1_occupancy;
+    if (n1_occupancy >= 1 && n1_occupancy <= 4) tuning().n1_occupancy = n1_occupancy;
     if (force_loop >= 0) tuning().force_loop = force_loop != 0;
     return 0;
 }

@@ -219,8 +219,8 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
 int64_t acas2d_launch_count(void);
 
 /* Experiment knobs (process-wide; also settable through the environment variables
- * ACAS2D_N1_OCC and ACAS2D_FORCE_LOOP before the first call).  n1_occupancy: 3 or 4 resident
- * blocks per SM for the N_TRAFFIC == 1 kernel (other values: unchanged).  force_loop: 1 routes
+ * ACAS2D_N1_OCC and ACAS2D_FORCE_LOOP before the first call).  n1_occupancy: 1..4 resident
+ * blocks per SM for the N_TRAFFIC == 1 kernel (default 2; other values: unchanged).  force_loop: 1 routes
  * N_TRAFFIC > 1 to the one-thread-per-env kernel that the shared-memory tiled kernel is
  * checked against, 0 back to the tiled kernel, negative: unchanged. */
 int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop);

@@ -185,7 +185,7 @@ def test_tiled_kernel_equals_loop_kernel(cuda, n):
     assert torch.equal(a.episode_counters(), b.episode_counters())
 
 
-@pytest.mark.parametrize("stages,occ", [(2, 4), (3, 4), (4, 3), (5, 3)])
+@pytest.mark.parametrize("stages,occ", [(2, 2), (2, 4), (3, 1), (4, 3), (5, 3)])
 def test_tma_ring_kernel_equals_direct_kernel(cuda, stages, occ):
     """N_TRAFFIC == 1: the persistent kernel fed by the TMA bulk-copy ring and the direct
     one-thread-per-env kernel are the same function, bit for bit -- ragged batch (B % 256 != 0),
@@ -212,13 +212,13 @@ def test_tma_ring_kernel_equals_direct_kernel(cuda, stages, occ):
             assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(a.flags, b.flags)
             assert torch.equal(a.term_obs[da], b.term_obs[db]) and torch.equal(a.ep_length[da], b.ep_length[db])
     finally:
-        lib.acas2d_set_tuning(3, -1); lib.acas2d_set_n1_kernel(1, 2)
+        lib.acas2d_set_tuning(2, -1); lib.acas2d_set_n1_kernel(1, 2)
     assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.thot, b.thot)
     assert torch.equal(a.episode_idx, b.episode_idx) and torch.equal(a.episode_counters(), b.episode_counters())
     assert a.episode_counters()[0].item() > 1000
 
 
-@pytest.mark.parametrize("stages,occ", [(3, 4), (5, 3)])
+@pytest.mark.parametrize("stages,occ", [(2, 2), (5, 3)])
 def test_tma_ring_stress_at_full_size(cuda, stages, occ):
     """Regression for a cross-proxy WAR race: at 4 Mi envs every CTA refills each ring stage ~10 times
     per launch; without `fence.proxy.async` before the barrier whole warps read the next tile's
@@ -239,7 +239,7 @@ def test_tma_ring_stress_at_full_size(cuda, stages, occ):
             assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux), t
             assert torch.equal(a.obs.view(torch.int32), b.obs.view(torch.int32)) and torch.equal(a.reward, b.reward), t
     finally:
-        lib.acas2d_set_tuning(3, -1); lib.acas2d_set_n1_kernel(1, 2)
+        lib.acas2d_set_tuning(2, -1); lib.acas2d_set_n1_kernel(1, 2)
 
 
 def test_sharding_invariance_and_determinism(cuda):
