@@ -126,6 +126,15 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
 
     const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full);
     const uint64_t pol = ACAS2D_LOAD_HINT ? l2_evict_first_policy() : 0;
+    // tile schedule: round-robin over the grid (the CTAs sweep one contiguous window of HBM together), or
+    // -DACAS2D_BLOCKED_TILES: each CTA streams through its own contiguous range (experiment)
+#ifdef ACAS2D_BLOCKED_TILES
+    const long long per_cta = (full_tiles + gridDim.x - 1) / gridDim.x;
+    const long long tile_first = (long long)blockIdx.x * per_cta, tile_step = 1;
+    const long long tile_end = (tile_first + per_cta < full_tiles) ? tile_first + per_cta : full_tiles;
+#else
+    const long long tile_first = blockIdx.x, tile_step = gridDim.x, tile_end = full_tiles;
+#endif
     auto issue = [&](long long tile, int s) {
         const uint32_t base = smem_base + s * kStageBytes, bar = full_base + 8 * s;
         const long long e0 = tile * kTileEnvs;
@@ -139,15 +148,15 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (tile < full_tiles) issue(tile, s);
+            const long long tile = tile_first + (long long)s * tile_step;
+            if (tile < tile_end) issue(tile, s);
         }
     }
 
     Tally tally;
     tally_clear(tally);
     int it = 0;
-    for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
         const int s = it % STAGES;
         mbar_wait(full_base + 8 * s, (unsigned)(it / STAGES) & 1u);
         const unsigned char *base = smem + s * kStageBytes;
@@ -162,8 +171,8 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();                                   // every thread has drained stage s
         if (tid == 0) {
-            const long long next = tile + (long long)STAGES * gridDim.x;
-            if (next < full_tiles) issue(next, s);
+            const long long next = tile + (long long)STAGES * tile_step;
+            if (next < tile_end) issue(next, s);
         }
         const int64_t i = tile * kTileEnvs + tid;
         Env1 e;
