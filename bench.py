@@ -377,6 +377,22 @@ def run_ours(args):
         other["config2_4096_envs_cuda_graph"] = {"value": world * 4096 * 200 * 10 / (ms_s * 1e-3), "unit": UNIT,
                                                  "note": "BASELINE config 2 batch: launch-bound, 200-step CUDA graph replay"}
 
+        if world == 1:
+            # PPO learner (BASELINE config 5): one epoch of 32 minibatch gradient steps, this repo's
+            # kernels vs the same arithmetic in torch autograd (both replayed from CUDA graphs)
+            from gym_ACAS2D import ppo as _ppo
+            n_l, mbs = 131072, 32
+            data = [torch.rand(n_l, 8, device=dev) * 2 - 1, torch.randn(n_l, device=dev), -torch.rand(n_l, device=dev) - 0.5,
+                    torch.randn(n_l, device=dev), torch.randn(n_l, device=dev)]
+            for name, cls in (("fused_kernels", _ppo.FusedLearner), ("torch_autograd_cuda_graph", _ppo.TorchLearner)):
+                learner = cls(dev, None, None, cuda_graph=True)
+                learner.bind(*data, mbs)
+                learner.epoch()
+                ms_l = timed(lambda k: learner.epoch(), 3)
+                other["ppo_learner_" + name] = {
+                    "us_per_gradient_step": 1e3 * ms_l / (3 * mbs), "minibatch": n_l // mbs,
+                    "note": "advantage normalisation + forward/backward of actor and critic + grad-norm clip + Adam"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,

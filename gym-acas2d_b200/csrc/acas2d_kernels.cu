@@ -31,6 +31,7 @@
 #include "acas2d_env.cuh"
 #include "acas2d_dev.cuh"
 #include "acas2d_policy_tc.cuh"
+#include "acas2d_ppo.cuh"
 
 namespace {
 
@@ -50,9 +51,9 @@ int check_args(const acas2d_params *p, const acas2d_state *s)
     return 0;
 }
 
-int finish_launch()
+int finish_launch(int kernels = 1)
 {
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_launches.fetch_add(kernels, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
 
@@ -997,6 +998,89 @@ int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed, uint6
     if (state->num_envs <= 0) return state->num_envs < 0 ? ACAS2D_E_BAD_SIZE : 0;
     random_actions_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
         state->num_envs, state->env_id_offset, action_seed, step_index, actions);
+    return finish_launch();
+}
+
+// ---------------------------------------------------------------- PPO learner (acas2d_ppo.cuh)
+int acas2d_ppo_values(const float *params, const float *obs, int64_t n, float *values, void *stream)
+{
+    if (n < 0) return ACAS2D_E_BAD_SIZE;
+    if (n == 0) return 0;
+    if (!params || !obs || !values) return ACAS2D_E_NULL;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(ppo_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpoValSmemBytes);
+        if (err != cudaSuccess) return (int)err;
+        attr_set[dev & 63] = true;
+    }
+    long long grid = (long long)sms * 2;
+    const long long tiles = (n + kPpoTile - 1) / kPpoTile;
+    if (grid > tiles) grid = tiles;
+    ppo_values_kernel<<<(unsigned)grid, kPpoThreads, kPpoValSmemBytes, (cudaStream_t)stream>>>(params, obs, n, values);
+    return finish_launch();
+}
+
+int acas2d_ppo_gae(const acas2d_ppo_config *cfg, const float *rewards, const uint8_t *dones, const float *values,
+                   int32_t n_steps, int64_t num_envs, float *advantages, float *returns, void *stream)
+{
+    if (n_steps < 0 || num_envs < 0) return ACAS2D_E_BAD_SIZE;
+    if (n_steps == 0 || num_envs == 0) return 0;
+    if (!cfg || !rewards || !dones || !values || !advantages || !returns) return ACAS2D_E_NULL;
+    ppo_gae_kernel<<<grid_for(num_envs), kBlock, 0, (cudaStream_t)stream>>>(
+        rewards, dones, values, n_steps, num_envs, cfg->gamma, cfg->gae_lambda, advantages, returns);
+    return finish_launch();
+}
+
+int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const float *obs, const float *actions,
+                    const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
+                    int64_t minibatch, float *workspace, float *grad, float *loss_stats, int32_t *adam_step,
+                    void *stream)
+{
+    if (minibatch <= 0) return ACAS2D_E_BAD_SIZE;
+    if (!cfg || !params || !obs || !actions || !old_logp || !advantages || !returns || !workspace || !grad)
+        return ACAS2D_E_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpoSmemBytes);
+        if (err != cudaSuccess) return (int)err;
+        attr_set[dev & 63] = true;
+    }
+    float *adv_stats = workspace, *partials = workspace + 4;
+    int kernels = 2;
+    if (cfg->normalize_advantage) {
+        ppo_adv_stats_kernel<<<1, 1024, 0, st>>>(advantages, indices, minibatch, adv_stats);
+        ++kernels;
+    }
+    const int64_t tiles = (minibatch + kPpoTile - 1) / kPpoTile;
+    const int ctas = (int)(tiles < kPpoMaxCtas ? tiles : kPpoMaxCtas);
+    PpoBatch b;
+    b.obs = obs; b.actions = actions; b.old_logp = old_logp; b.adv = advantages; b.ret = returns;
+    b.idx = indices; b.mb = minibatch;
+    ppo_grad_kernel<<<dim3((unsigned)ctas, 2), kPpoThreads, kPpoSmemBytes, st>>>(
+        params, b, cfg->normalize_advantage ? adv_stats : nullptr, cfg->clip_range, cfg->vf_coef, partials);
+    ppo_reduce_kernel<<<(kPpoParams + 255) / 256, 256, 0, st>>>(partials, ctas, cfg->ent_coef, 1.0f / (float)minibatch,
+                                                                grad, loss_stats, adam_step);
+    return finish_launch(kernels);
+}
+
+int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *grad, float grad_scale,
+                    float *adam_m, float *adam_v, const int32_t *adam_step, float *loss_stats, void *stream)
+{
+    if (!cfg || !params || !grad || !adam_m || !adam_v || !adam_step) return ACAS2D_E_NULL;
+    ppo_adam_kernel<<<(kPpoParams + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        params, grad, grad_scale, adam_m, adam_v, adam_step, cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps,
+        cfg->max_grad_norm, loss_stats);
     return finish_launch();
 }
 

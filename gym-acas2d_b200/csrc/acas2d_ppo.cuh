@@ -1,0 +1,496 @@
+// acas2d_ppo.cuh -- PPO learner kernels for the reference's agent (BASELINE config 5).
+//
+// The reference trains stable_baselines3.PPO('MlpPolicy', env, seed=13) (gym_ACAS2D/training_main.py:44-52);
+// the hyper-parameters stored in models/best_model_1048576_11/best_model.zip/data are the SB3 1.1.0 defaults:
+// separate 8 -> 64 -> 64 tanh actor and critic, state-independent log_std, clipped surrogate (clip 0.2) on
+// minibatch-normalised advantages, 0.5 * MSE value loss, no entropy bonus, global grad-norm clip 0.5, Adam.
+// SB3 is not vendored by the reference; what is restated here is SB3 1.1.0's published PPO.train() arithmetic
+// (ppo.py there), and the numerics reference in tests/ is the same loss written in plain torch float32
+// (gym_ACAS2D/ppo.py: reference_loss) differentiated by autograd.
+//
+// One gradient step = three small kernels (+ one optional all-reduce between the last two):
+//   ppo_adv_stats_kernel  mean / unbiased std of the minibatch's advantages (one CTA, two passes)
+//   ppo_grad_kernel       forward + backward of BOTH networks over the minibatch: grid (G, 2), blockIdx.y
+//                         picks actor or critic (their losses do not interact), each CTA walks 64-sample
+//                         tiles, everything in shared memory, weight gradients accumulated in registers
+//                         across its tiles, one partial-gradient row per CTA
+//   ppo_reduce_kernel     fixed-order sum of the partial rows -> grad[9612], loss statistics, Adam step count
+//   ppo_adam_kernel       global norm (recomputed per CTA, same order everywhere), clip, Adam
+// The matrices are 64-wide: a minibatch step is ~0.1 GFLOP, launch/latency-bound, so this is float32 on
+// the CUDA cores (bit-comparable with the torch float32 reference) rather than TF32 tensor-core code.
+// Everything is deterministic: no floating-point atomics.
+#pragma once
+
+#include "acas2d_policy.cuh"
+#include "acas2d_dev.cuh"
+
+namespace acas2d {
+
+constexpr int kPpoLogStd = 2 * kPolFloats;          // parameter block: actor | critic | log_std | 3 pad
+constexpr int kPpoParams = ACAS2D_PPO_PARAM_FLOATS;
+constexpr int kPpoPartial = ACAS2D_PPO_PARTIAL_FLOATS;
+constexpr int kPpoMaxCtas = ACAS2D_PPO_MAX_CTAS;
+constexpr int kPpoTile = 64, kPpoThreads = 256;
+constexpr int kPpoLd = 68;                          // shared-memory row stride of the 64-wide matrices (16-byte rows, bank-skewed)
+constexpr int kPpoLdW1 = 12;                        // same for W1 rows (8 wide)
+// partial row tail: dlog_std | sum pg term | sum value term | sum approx-kl term | clipped count
+constexpr int kPpoStatBase = kPolFloats;
+static_assert(kPpoParams == 2 * kPolFloats + 4 && kPpoPartial >= kPolFloats + 8, "PPO block sizes");
+
+struct PpoBatch {
+    const float *obs;        // [n][8]
+    const float *actions;    // [n]   unclipped samples
+    const float *old_logp;   // [n]
+    const float *adv;        // [n]
+    const float *ret;        // [n]
+    const int64_t *idx;      // [mb] rows of this minibatch (nullptr: 0..mb-1)
+    int64_t mb;
+};
+
+// shared-memory plan of ppo_grad_kernel (floats)
+constexpr int kPpoSmW2 = 0, kPpoSmW2T = kPpoSmW2 + 64 * kPpoLd, kPpoSmW1 = kPpoSmW2T + 64 * kPpoLd,
+              kPpoSmB1 = kPpoSmW1 + 64 * kPpoLdW1, kPpoSmB2 = kPpoSmB1 + 64, kPpoSmW3 = kPpoSmB2 + 64,
+              kPpoSmX = kPpoSmW3 + 64, kPpoSmH1 = kPpoSmX + kPpoTile * 8, kPpoSmC = kPpoSmH1 + kPpoTile * kPpoLd,
+              kPpoSmDy = kPpoSmC + kPpoTile * kPpoLd, kPpoSmRed = kPpoSmDy + kPpoTile,
+              kPpoSmFloats = kPpoSmRed + 2 * kPpoThreads;
+constexpr int kPpoSmemBytes = kPpoSmFloats * 4;
+
+#if defined(__CUDACC__)
+
+// acc[q][r] += sum_{k<K} A[(mg + 16 q) * lda + k] * B[(ng + 16 r) * ldb + k]: both operands are read as
+// 128-bit words along k.  Rows are dealt to the 16 x 16 thread grid interleaved (row = group + 16 q), so
+// the 8 threads of a quarter warp read 8 consecutive rows of B -- with a row stride of 68 (or 12) floats
+// those fall in 8 distinct 4-bank groups -- while A is a 2-address broadcast.
+template <int K>
+__device__ __forceinline__ void ppo_gemm_nt(const float *A, int lda, const float *B, int ldb, int mg, int ng,
+                                            float (&acc)[4][4])
+{
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = *(const float4 *)(A + (mg + 16 * q) * lda + k);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) b[r] = *(const float4 *)(B + (ng + 16 * r) * ldb + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float s = acc[q][r];
+                s = fmaf(a[q].x, b[r].x, s); s = fmaf(a[q].y, b[r].y, s);
+                s = fmaf(a[q].z, b[r].z, s); s = fmaf(a[q].w, b[r].w, s);
+                acc[q][r] = s;
+            }
+    }
+}
+
+__device__ __forceinline__ float ppo_block_sum(float v, float *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.0f;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) s += red[w];            // same order in every thread
+    return s;
+}
+
+__device__ __forceinline__ double ppo_block_sum_d(double v, double *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    return s;
+}
+
+// stats[0] = mean, stats[1] = 1 / (std + 1e-8) of adv[idx[0..mb)], std with Bessel's correction
+// (SB3 ppo.py: advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)).
+__global__ void __launch_bounds__(1024)
+ppo_adv_stats_kernel(const float *__restrict__ adv, const int64_t *__restrict__ idx, const int64_t mb, float *stats)
+{
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t k = threadIdx.x; k < mb; k += blockDim.x) s += (double)adv[idx ? idx[k] : k];
+    const double mean = ppo_block_sum_d(s, red) / (double)mb;
+    double q = 0.0;
+    for (int64_t k = threadIdx.x; k < mb; k += blockDim.x) {
+        const double d = (double)adv[idx ? idx[k] : k] - mean;
+        q += d * d;
+    }
+    const double var = ppo_block_sum_d(q, red) / (double)(mb > 1 ? mb - 1 : 1);
+    if (threadIdx.x == 0) {
+        stats[0] = (float)mean;
+        stats[1] = 1.0f / ((float)sqrt(var) + 1e-8f);
+    }
+}
+
+__global__ void __launch_bounds__(kPpoThreads, 2)
+ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const float *__restrict__ adv_stats,
+                const float clip_range, const float vf_coef, float *__restrict__ partials)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *sW2 = sm + kPpoSmW2, *sW2T = sm + kPpoSmW2T, *sW1 = sm + kPpoSmW1, *sb1 = sm + kPpoSmB1,
+          *sb2 = sm + kPpoSmB2, *sw3 = sm + kPpoSmW3, *sX = sm + kPpoSmX, *sH1 = sm + kPpoSmH1, *sC = sm + kPpoSmC,
+          *sdy = sm + kPpoSmDy, *sred = sm + kPpoSmRed;
+    const int t = threadIdx.x;
+    const int net = blockIdx.y;                                   // 0 = actor, 1 = critic
+    const float *w = params + net * kPolFloats;
+    const int mg = t >> 4, ng = t & 15;                           // 16 x 16 thread grid of the 64 x 64 products
+
+    for (int e = t; e < 64 * 64; e += kPpoThreads) {              // W2[j][i], rows as SB3 stores them, and its transpose
+        const int j = e >> 6, i = e & 63;
+        const float v = w[kPolW2 + e];
+        sW2[j * kPpoLd + i] = v;
+        sW2T[i * kPpoLd + j] = v;
+    }
+    for (int e = t; e < 64 * 8; e += kPpoThreads) sW1[(e >> 3) * kPpoLdW1 + (e & 7)] = w[kPolW1 + e];
+    if (t < 64) { sb1[t] = w[kPolB1 + t]; sb2[t] = w[kPolB2 + t]; sw3[t] = w[kPolW3 + t]; }
+    const float b3 = w[kPolB3];
+    const float log_std = params[kPpoLogStd];
+    const float inv_var = __expf(-2.0f * log_std);
+    const float adv_mean = adv_stats ? adv_stats[0] : 0.0f, adv_scale = adv_stats ? adv_stats[1] : 1.0f;
+    const float inv_mb = 1.0f / (float)b.mb;
+
+    // gradient accumulators, kept in registers across this CTA's tiles
+    float gW2[4][4] = {};                    // dW2[4 jg + q][4 ig + r]   (jg = t >> 4, ig = t & 15)
+    float gW1[2] = {0.0f, 0.0f};             // dW1[t >> 2][2 (t & 3) + {0, 1}]
+    float gb1 = 0.0f, gb2 = 0.0f, gw3 = 0.0f, gb3 = 0.0f;        // t < 64: unit t; gb3: t == 0
+    float st_dls = 0.0f, st_pg = 0.0f, st_v = 0.0f, st_kl = 0.0f, st_clip = 0.0f;
+    __syncthreads();
+
+    const int64_t ntiles = (b.mb + kPpoTile - 1) / kPpoTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- gather the tile's observation rows (zero rows past the end of the minibatch)
+        if (t < 2 * kPpoTile) {
+            const int s = t >> 1, h = t & 1;
+            const int64_t k = tile * kPpoTile + s;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (k < b.mb) v = ((const float4 *)b.obs)[2 * (b.idx ? b.idx[k] : k) + h];
+            *(float4 *)(sX + s * 8 + 4 * h) = v;
+        }
+        __syncthreads();
+
+        // ---- layer 1: H1[s][j] = tanh(b1[j] + sum_c X[s][c] W1[j][c])
+        {
+            float acc[4][4] = {};
+            ppo_gemm_nt<8>(sX, 8, sW1, kPpoLdW1, mg, ng, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb1[ng + 16 * r]);
+        }
+        __syncthreads();
+
+        // ---- layer 2: H2[s][j] = tanh(b2[j] + sum_i H1[s][i] W2[j][i])  -> sC
+        {
+            float acc[4][4] = {};
+            ppo_gemm_nt<64>(sH1, kPpoLd, sW2, kPpoLd, mg, ng, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb2[ng + 16 * r]);
+        }
+        __syncthreads();
+
+        // ---- output unit and the loss derivative of each sample (4 lanes per sample)
+        {
+            const int s = t >> 2, part = t & 3;
+            float y = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) y = fmaf(sw3[part * 16 + jj], sC[s * kPpoLd + part * 16 + jj], y);
+            y += __shfl_xor_sync(kFull, y, 1);
+            y += __shfl_xor_sync(kFull, y, 2);
+            y += b3;
+            if (part == 0) {
+                const int64_t k = tile * kPpoTile + s;
+                float dy = 0.0f;
+                if (k < b.mb) {
+                    const int64_t row = b.idx ? b.idx[k] : k;
+                    if (net == 0) {
+                        // SB3 ppo.py train(): ratio = exp(log_prob - old_log_prob); policy_loss =
+                        // -mean(min(adv * ratio, adv * clamp(ratio, 1 - clip, 1 + clip)))
+                        const float an = (b.adv[row] - adv_mean) * adv_scale;
+                        const float diff = b.actions[row] - y;
+                        const float z2 = diff * diff * inv_var;
+                        const float logp = -0.5f * z2 - log_std - 0.9189385332046727f;
+                        const float lr = logp - b.old_logp[row];
+                        const float ratio = __expf(lr);
+                        const float rc = fminf(fmaxf(ratio, 1.0f - clip_range), 1.0f + clip_range);
+                        st_pg += -fminf(an * ratio, an * rc);
+                        st_kl += (ratio - 1.0f) - lr;
+                        st_clip += (fabsf(ratio - 1.0f) > clip_range) ? 1.0f : 0.0f;
+                        const bool cut = (an > 0.0f && ratio > 1.0f + clip_range) || (an < 0.0f && ratio < 1.0f - clip_range);
+                        const float g = cut ? 0.0f : -an * ratio * inv_mb;        // d loss / d logp
+                        dy = g * diff * inv_var;                                    // d logp / d mean
+                        st_dls += g * (z2 - 1.0f);                                  // d logp / d log_std
+                    } else {
+                        // value_loss = F.mse_loss(returns, values), weighted by vf_coef
+                        const float d = y - b.ret[row];
+                        st_v += d * d;
+                        dy = vf_coef * 2.0f * d * inv_mb;
+                    }
+                }
+                sdy[s] = dy;
+            }
+        }
+        __syncthreads();
+
+        // ---- dw3, db3; dZ2 = dy * w3 * (1 - H2^2) in place of H2; db2 (column sums: 4 x 16 samples per unit)
+        {
+            const int j = t & 63, part = t >> 6;
+            const float w3j = sw3[j];
+            float pw3 = 0.0f, pb2 = 0.0f;
+#pragma unroll 4
+            for (int s = part * 16; s < part * 16 + 16; ++s) {
+                const float h = sC[s * kPpoLd + j], dyv = sdy[s];
+                pw3 = fmaf(dyv, h, pw3);
+                const float dz = dyv * w3j * (1.0f - h * h);
+                sC[s * kPpoLd + j] = dz;
+                pb2 += dz;
+            }
+            sred[t] = pw3;
+            sred[kPpoThreads + t] = pb2;
+        }
+        __syncthreads();
+        if (t < 64) {
+            gw3 += (sred[t] + sred[64 + t]) + (sred[128 + t] + sred[192 + t]);
+            gb2 += (sred[kPpoThreads + t] + sred[kPpoThreads + 64 + t]) +
+                   (sred[kPpoThreads + 128 + t] + sred[kPpoThreads + 192 + t]);
+        }
+        if (t < 32) {
+            float v = sdy[t] + sdy[t + 32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (t == 0) gb3 += v;
+        }
+
+        // ---- dW2[j][i] += sum_s dZ2[s][j] H1[s][i]: outer products, contiguous 4 x 4 ownership, two
+        //      128-bit loads per sample (dZ2 row: broadcast; H1 row: consecutive words)
+        {
+            const int j0 = 4 * mg, i0 = 4 * ng;
+#pragma unroll 4
+            for (int s = 0; s < kPpoTile; ++s) {
+                const float4 a = *(const float4 *)(sC + s * kPpoLd + j0);
+                const float4 h = *(const float4 *)(sH1 + s * kPpoLd + i0);
+                gW2[0][0] = fmaf(a.x, h.x, gW2[0][0]); gW2[0][1] = fmaf(a.x, h.y, gW2[0][1]);
+                gW2[0][2] = fmaf(a.x, h.z, gW2[0][2]); gW2[0][3] = fmaf(a.x, h.w, gW2[0][3]);
+                gW2[1][0] = fmaf(a.y, h.x, gW2[1][0]); gW2[1][1] = fmaf(a.y, h.y, gW2[1][1]);
+                gW2[1][2] = fmaf(a.y, h.z, gW2[1][2]); gW2[1][3] = fmaf(a.y, h.w, gW2[1][3]);
+                gW2[2][0] = fmaf(a.z, h.x, gW2[2][0]); gW2[2][1] = fmaf(a.z, h.y, gW2[2][1]);
+                gW2[2][2] = fmaf(a.z, h.z, gW2[2][2]); gW2[2][3] = fmaf(a.z, h.w, gW2[2][3]);
+                gW2[3][0] = fmaf(a.w, h.x, gW2[3][0]); gW2[3][1] = fmaf(a.w, h.y, gW2[3][1]);
+                gW2[3][2] = fmaf(a.w, h.z, gW2[3][2]); gW2[3][3] = fmaf(a.w, h.w, gW2[3][3]);
+            }
+        }
+        __syncthreads();                                   // all reads of H1 done before it is overwritten
+
+        // ---- dZ1[s][i] = (sum_j dZ2[s][j] W2[j][i]) * (1 - H1[s][i]^2), in place of H1
+        {
+            float acc[4][4] = {};
+            ppo_gemm_nt<64>(sC, kPpoLd, sW2T, kPpoLd, mg, ng, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float *p = sH1 + (mg + 16 * q) * kPpoLd + ng + 16 * r;
+                    const float h = *p;
+                    *p = acc[q][r] * (1.0f - h * h);
+                }
+        }
+        __syncthreads();
+
+        // ---- db1 (column sums of dZ1) and dW1[j][c] += sum_s dZ1[s][j] X[s][c]
+        {
+            const int j = t & 63, part = t >> 6;
+            float pb1 = 0.0f;
+#pragma unroll 4
+            for (int s = part * 16; s < part * 16 + 16; ++s) pb1 += sH1[s * kPpoLd + j];
+            sred[t] = pb1;
+            const int jw = t >> 2, c0 = 2 * (t & 3);
+#pragma unroll 4
+            for (int s = 0; s < kPpoTile; ++s) {
+                const float d = sH1[s * kPpoLd + jw];
+                const float2 x = *(const float2 *)(sX + s * 8 + c0);
+                gW1[0] = fmaf(d, x.x, gW1[0]);
+                gW1[1] = fmaf(d, x.y, gW1[1]);
+            }
+        }
+        __syncthreads();
+        if (t < 64) gb1 += (sred[t] + sred[64 + t]) + (sred[128 + t] + sred[192 + t]);
+        __syncthreads();                                   // sred / sX / sH1 are rewritten by the next tile
+    }
+
+    // ---- this CTA's partial row
+    float *row = partials + ((size_t)net * gridDim.x + blockIdx.x) * kPpoPartial;
+    {
+        const int j0 = 4 * mg, i0 = 4 * ng;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *(float4 *)(row + kPolW2 + (j0 + q) * 64 + i0) = make_float4(gW2[q][0], gW2[q][1], gW2[q][2], gW2[q][3]);
+        *(float2 *)(row + kPolW1 + (t >> 2) * 8 + 2 * (t & 3)) = make_float2(gW1[0], gW1[1]);
+    }
+    if (t < 64) { row[kPolB1 + t] = gb1; row[kPolB2 + t] = gb2; row[kPolW3 + t] = gw3; }
+    if (t == 0) { row[kPolB3] = gb3; row[kPolB3 + 1] = 0.0f; row[kPolB3 + 2] = 0.0f; row[kPolB3 + 3] = 0.0f; }
+    const float s0 = ppo_block_sum(st_dls, sred), s1 = ppo_block_sum(st_pg, sred), s2 = ppo_block_sum(st_v, sred),
+                s3 = ppo_block_sum(st_kl, sred), s4 = ppo_block_sum(st_clip, sred);
+    if (t == 0) {
+        row[kPpoStatBase + 0] = s0; row[kPpoStatBase + 1] = s1; row[kPpoStatBase + 2] = s2;
+        row[kPpoStatBase + 3] = s3; row[kPpoStatBase + 4] = s4;
+    }
+}
+
+// grad[p] = sum over the CTAs' partial rows, in row order.  loss_stats: 0 policy loss, 1 value loss (MSE),
+// 2 approx KL, 3 clip fraction (SB3's logged quantities); 4 = gradient norm (written by ppo_adam_kernel).
+__global__ void __launch_bounds__(256)
+ppo_reduce_kernel(const float *__restrict__ partials, const int ctas, const float ent_coef, const float inv_mb,
+                  float *__restrict__ grad, float *__restrict__ loss_stats, int32_t *adam_step)
+{
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p < kPpoParams) {
+        float s = 0.0f;
+        if (p < 2 * kPolFloats) {
+            const int net = p >= kPolFloats, q = p - net * kPolFloats;
+            const float *src = partials + (size_t)net * ctas * kPpoPartial + q;
+            for (int c = 0; c < ctas; ++c) s += src[(size_t)c * kPpoPartial];
+        } else if (p == kPpoLogStd) {
+            for (int c = 0; c < ctas; ++c) s += partials[(size_t)c * kPpoPartial + kPpoStatBase];
+            s -= ent_coef;                    // entropy of N(., sigma) = log_std + const; loss has -ent_coef * entropy
+        }
+        grad[p] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x >= 1 && threadIdx.x <= 4 && loss_stats) {
+        const int f = threadIdx.x;            // pg / value / kl / clip
+        const int net = (f == 2) ? 1 : 0;
+        float s = 0.0f;
+        for (int c = 0; c < ctas; ++c) s += partials[((size_t)net * ctas + c) * kPpoPartial + kPpoStatBase + f];
+        loss_stats[f - 1] = s * inv_mb;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && adam_step) *adam_step += 1;
+}
+
+// torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.Adam(lr, betas, eps).step(), on
+// grad * grad_scale (1/world after a SUM all-reduce).  Every CTA recomputes the global norm in the same
+// order, so all of them apply the same clip coefficient without a grid-wide barrier.
+__global__ void __launch_bounds__(256)
+ppo_adam_kernel(float *__restrict__ params, const float *__restrict__ grad, const float grad_scale,
+                float *__restrict__ m, float *__restrict__ v, const int32_t *__restrict__ adam_step,
+                const float lr, const float beta1, const float beta2, const float eps, const float max_grad_norm,
+                float *__restrict__ loss_stats)
+{
+    __shared__ float red[8];
+    float q = 0.0f;
+    for (int p = threadIdx.x; p < kPpoParams; p += 256) {
+        const float g = grad[p] * grad_scale;
+        q = fmaf(g, g, q);
+    }
+    const float norm = sqrtf(ppo_block_sum(q, red));
+    float coef = (max_grad_norm > 0.0f) ? max_grad_norm / (norm + 1e-6f) : 1.0f;
+    coef = fminf(coef, 1.0f);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss_stats) loss_stats[4] = norm;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p > kPpoLogStd) return;
+    const int step = *adam_step;
+    const float g = grad[p] * grad_scale * coef;
+    const float mn = beta1 * m[p] + (1.0f - beta1) * g;
+    const float vn = beta2 * v[p] + (1.0f - beta2) * g * g;
+    m[p] = mn; v[p] = vn;
+    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    const float denom = sqrtf(vn) / sqrtf(bc2) + eps;
+    params[p] -= (lr / bc1) * (mn / denom);
+}
+
+// Critic forward over n observation rows (the value head of SB3's MlpPolicy: mlp_extractor.value_net +
+// value_net): the forward half of ppo_grad_kernel, 64-row tiles, persistent CTAs.
+constexpr int kPpoValSmFloats = 64 * kPpoLd + 64 * kPpoLdW1 + 3 * 64 + kPpoTile * 8 + 2 * kPpoTile * kPpoLd;
+constexpr int kPpoValSmemBytes = kPpoValSmFloats * 4;
+
+__global__ void __launch_bounds__(kPpoThreads, 2)
+ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ obs, const int64_t n, float *__restrict__ values)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *sW2 = sm, *sW1 = sW2 + 64 * kPpoLd, *sb1 = sW1 + 64 * kPpoLdW1, *sb2 = sb1 + 64, *sw3 = sb2 + 64,
+          *sX = sw3 + 64, *sH1 = sX + kPpoTile * 8, *sC = sH1 + kPpoTile * kPpoLd;
+    const int t = threadIdx.x, mg = t >> 4, ng = t & 15;
+    const float *w = params + kPolFloats;
+    for (int e = t; e < 64 * 64; e += kPpoThreads) sW2[(e >> 6) * kPpoLd + (e & 63)] = w[kPolW2 + e];
+    for (int e = t; e < 64 * 8; e += kPpoThreads) sW1[(e >> 3) * kPpoLdW1 + (e & 7)] = w[kPolW1 + e];
+    if (t < 64) { sb1[t] = w[kPolB1 + t]; sb2[t] = w[kPolB2 + t]; sw3[t] = w[kPolW3 + t]; }
+    const float b3 = w[kPolB3];
+    __syncthreads();
+    const int64_t ntiles = (n + kPpoTile - 1) / kPpoTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (t < 2 * kPpoTile) {
+            const int64_t k = tile * kPpoTile + (t >> 1);
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (k < n) v = __ldcs((const float4 *)obs + 2 * k + (t & 1));
+            *(float4 *)(sX + (t >> 1) * 8 + 4 * (t & 1)) = v;
+        }
+        __syncthreads();
+        {
+            float acc[4][4] = {};
+            ppo_gemm_nt<8>(sX, 8, sW1, kPpoLdW1, mg, ng, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb1[ng + 16 * r]);
+        }
+        __syncthreads();
+        {
+            float acc[4][4] = {};
+            ppo_gemm_nt<64>(sH1, kPpoLd, sW2, kPpoLd, mg, ng, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb2[ng + 16 * r]);
+        }
+        __syncthreads();
+        {
+            const int s = t >> 2, part = t & 3;
+            float y = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) y = fmaf(sw3[part * 16 + jj], sC[s * kPpoLd + part * 16 + jj], y);
+            y += __shfl_xor_sync(kFull, y, 1);
+            y += __shfl_xor_sync(kFull, y, 2);
+            const int64_t k = tile * kPpoTile + s;
+            if (part == 0 && k < n) values[k] = y + b3;
+        }
+        __syncthreads();
+    }
+}
+
+// Generalised advantage estimation over a [T][B] rollout (SB3 RolloutBuffer.compute_returns_and_advantage):
+// values[T + 1][B] (row T bootstraps), dones[t][b] = the step t ended its episode.  One thread per env.
+__global__ void __launch_bounds__(256)
+ppo_gae_kernel(const float *__restrict__ rewards, const uint8_t *__restrict__ dones, const float *__restrict__ values,
+               const int T, const int64_t B, const float gamma, const float lam, float *__restrict__ adv,
+               float *__restrict__ ret)
+{
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= B) return;
+    float last = 0.0f, vnext = values[(int64_t)T * B + e];
+    for (int t = T - 1; t >= 0; --t) {
+        const int64_t k = (int64_t)t * B + e;
+        const float nonterminal = dones[k] ? 0.0f : 1.0f;
+        const float vt = values[k];
+        const float delta = rewards[k] + gamma * vnext * nonterminal - vt;
+        last = delta + gamma * lam * nonterminal * last;
+        adv[k] = last;
+        ret[k] = last + vt;
+        vnext = vt;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace acas2d

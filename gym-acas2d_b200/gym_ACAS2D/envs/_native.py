@@ -16,7 +16,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 CSRC_DIR = os.path.join(_PKG_ROOT, "csrc")
 REPO_ROOT = os.path.dirname(_PKG_ROOT)
 LIB_PATH = os.path.join(CSRC_DIR, "libacas2d_b200.so")
-SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh", "acas2d_policy_tc.cuh", "acas2d_dev.cuh")
+SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh", "acas2d_policy_tc.cuh", "acas2d_dev.cuh", "acas2d_ppo.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -29,10 +29,16 @@ STAT_FX_SCALE = 1048576.0
 FLAG_COLLISION, FLAG_GOAL, FLAG_TIMEOUT, FLAG_DONE, FLAG_OOB = 1, 2, 4, 8, 16
 STEPS_RESIDUAL_BIT = 0x40000000
 POLICY_FLOATS = 4804
+PPO_PARAM_FLOATS = 2 * POLICY_FLOATS + 4
+PPO_LOG_STD = 2 * POLICY_FLOATS
+PPO_PARTIAL_FLOATS, PPO_MAX_CTAS = 4816, 148
+PPO_WORKSPACE_FLOATS = 4 + 2 * PPO_MAX_CTAS * PPO_PARTIAL_FLOATS
+PPO_LOSS_STATS = 8
 
 EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
-           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render")
+           "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render",
+           "acas2d_ppo_values", "acas2d_ppo_gae", "acas2d_ppo_grad", "acas2d_ppo_adam")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -56,6 +62,20 @@ class State(ctypes.Structure):
                 ("episode_idx", ctypes.c_void_p), ("min_sep", ctypes.c_void_p),
                 ("stats", ctypes.c_void_p),
                 ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_uint64)]
+
+
+class PpoConfig(ctypes.Structure):
+    """``acas2d_ppo_config``: SB3 1.1.0 PPO defaults (the reference's ``best_model.zip/data``)."""
+    _fields_ = [(n, ctypes.c_float) for n in (
+        "gamma", "gae_lambda", "clip_range", "vf_coef", "ent_coef", "max_grad_norm",
+        "lr", "beta1", "beta2", "adam_eps")] + [("normalize_advantage", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+    @classmethod
+    def sb3_defaults(cls, **over) -> "PpoConfig":
+        d = dict(gamma=0.99, gae_lambda=0.95, clip_range=0.2, vf_coef=0.5, ent_coef=0.0, max_grad_norm=0.5,
+                 lr=3e-4, beta1=0.9, beta2=0.999, adam_eps=1e-5, normalize_advantage=1)
+        d.update(over)
+        return cls(**d)
 
 
 class StepAux(ctypes.Structure):
@@ -98,6 +118,11 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_set_n1_kernel.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.acas2d_policy_step.argtypes = [PP, SP, vp, ctypes.c_float, vp, vp, vp, vp, vp, vp, AP, ctypes.c_int32,
                                        ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, vp]
+    CP = ctypes.POINTER(PpoConfig)
+    lib.acas2d_ppo_values.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
+    lib.acas2d_ppo_gae.argtypes = [CP, vp, vp, vp, ctypes.c_int32, ctypes.c_int64, vp, vp, vp]
+    lib.acas2d_ppo_grad.argtypes = [CP, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp]
+    lib.acas2d_ppo_adam.argtypes = [CP, vp, vp, ctypes.c_float, vp, vp, vp, vp, vp]
     return lib
 
 

@@ -215,6 +215,54 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
                        float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
                        uint64_t noise_seed, uint64_t step_index, int32_t tensor_cores, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PPO learner for the reference's agent (BASELINE config 5; gym_ACAS2D/training_main.py:44-52:
+ * stable_baselines3 PPO('MlpPolicy') with the SB3 1.1.0 defaults stored in best_model.zip/data).
+ *
+ * params float[ACAS2D_PPO_PARAM_FLOATS]: actor block (the ACAS2D_POLICY_FLOATS layout acas2d_policy_step
+ * reads, so `params` itself can be passed there as `weights`) | critic block in the same layout
+ * (mlp_extractor.value_net.{0,2}, value_net) | log_std | 3 pad.  All pointers are device pointers; every
+ * call is asynchronous on `stream`, allocates nothing and is CUDA-graph capturable. */
+#define ACAS2D_PPO_PARAM_FLOATS   (2 * ACAS2D_POLICY_FLOATS + 4)
+#define ACAS2D_PPO_PARTIAL_FLOATS 4816     /* one partial-gradient row */
+#define ACAS2D_PPO_MAX_CTAS       148      /* partial rows per network */
+#define ACAS2D_PPO_WORKSPACE_FLOATS (4 + 2 * ACAS2D_PPO_MAX_CTAS * ACAS2D_PPO_PARTIAL_FLOATS)
+#define ACAS2D_PPO_LOSS_STATS     8        /* policy loss, value loss, approx KL, clip fraction, grad norm, 3 spare */
+
+typedef struct acas2d_ppo_config {
+    float gamma, gae_lambda;                   /* 0.99, 0.95 */
+    float clip_range, vf_coef, ent_coef;       /* 0.2, 0.5, 0.0 */
+    float max_grad_norm;                       /* 0.5 (<= 0: no clipping) */
+    float lr, beta1, beta2, adam_eps;          /* 3e-4, 0.9, 0.999, 1e-5 */
+    int32_t normalize_advantage;               /* 1: (adv - mean) / (std + 1e-8) over the minibatch */
+    int32_t reserved;
+} acas2d_ppo_config;
+
+/* values[n] = critic(obs[n][8]). */
+int acas2d_ppo_values(const float *params, const float *obs, int64_t n, float *values, void *stream);
+
+/* SB3 RolloutBuffer.compute_returns_and_advantage on a [T][B] rollout: rewards float[T][B], dones
+ * uint8[T][B] (step t ended the episode), values float[T+1][B] -> advantages, returns float[T][B]. */
+int acas2d_ppo_gae(const acas2d_ppo_config *cfg, const float *rewards, const uint8_t *dones, const float *values,
+                   int32_t n_steps, int64_t num_envs, float *advantages, float *returns, void *stream);
+
+/* Gradient of  policy_loss + vf_coef * value_loss - ent_coef * entropy  (SB3 ppo.py train()) over the
+ * minibatch rows `indices` int64[minibatch] (NULL: rows 0..minibatch-1) of the flattened rollout
+ * (obs float[n][8], actions = unclipped samples, old_logp, advantages, returns: float[n]).
+ * workspace float[ACAS2D_PPO_WORKSPACE_FLOATS]; grad float[ACAS2D_PPO_PARAM_FLOATS] (overwritten);
+ * loss_stats float[ACAS2D_PPO_LOSS_STATS] or NULL; adam_step int32[1] or NULL, incremented by one.
+ * Deterministic (no floating-point atomics).  Launches three kernels (two without normalisation). */
+int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const float *obs, const float *actions,
+                    const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
+                    int64_t minibatch, float *workspace, float *grad, float *loss_stats, int32_t *adam_step,
+                    void *stream);
+
+/* clip_grad_norm_(max_grad_norm) + Adam step on grad * grad_scale (pass 1/world_size after a SUM
+ * all-reduce of `grad` over the data-parallel ranks, 1 otherwise).  adam_m / adam_v float[PARAM_FLOATS],
+ * adam_step = the counter acas2d_ppo_grad incremented.  loss_stats[4] receives the pre-clip norm. */
+int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *grad, float grad_scale,
+                    float *adam_m, float *adam_v, const int32_t *adam_step, float *loss_stats, void *stream);
+
 /* Kernels launched by this library since load (all entry points). */
 int64_t acas2d_launch_count(void);
 
