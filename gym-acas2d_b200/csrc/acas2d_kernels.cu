@@ -1002,6 +1002,7 @@ int acas2d_random_actions(const acas2d_state *state, uint64_t action_seed, uint6
 }
 
 // ---------------------------------------------------------------- PPO learner (acas2d_ppo.cuh)
+namespace { int ppo_prepare_device(); }
 int acas2d_ppo_values(const float *params, const float *obs, int64_t n, float *values, void *stream)
 {
     if (n < 0) return ACAS2D_E_BAD_SIZE;
@@ -1013,14 +1014,7 @@ int acas2d_ppo_values(const float *params, const float *obs, int64_t n, float *v
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(ppo_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpoValSmemBytes);
-        if (err != cudaSuccess) return (int)err;
-        attr_set[dev & 63] = true;
-    }
+    if (int e = ppo_prepare_device()) return e;
     long long grid = (long long)sms * 2;
     const long long tiles = (n + kPpoTile - 1) / kPpoTile;
     if (grid > tiles) grid = tiles;
@@ -1039,6 +1033,52 @@ int acas2d_ppo_gae(const acas2d_ppo_config *cfg, const float *rewards, const uin
     return finish_launch();
 }
 
+namespace {
+// Function attributes are per device; cudaFuncGetAttributes also forces the (lazily loaded) kernels in, so
+// that a first launch may happen inside a CUDA-graph capture.
+int ppo_prepare_device()
+{
+    static bool ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ready[dev & 63]) return 0;
+    cudaError_t err = cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpoSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(ppo_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpoValSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    cudaFuncAttributes fa;
+    if ((err = cudaFuncGetAttributes(&fa, ppo_reduce_kernel)) != cudaSuccess) return (int)err;
+    if ((err = cudaFuncGetAttributes(&fa, ppo_adam_kernel)) != cudaSuccess) return (int)err;
+    if ((err = cudaFuncGetAttributes(&fa, ppo_update_kernel)) != cudaSuccess) return (int)err;
+    if ((err = cudaFuncGetAttributes(&fa, ppo_gae_kernel)) != cudaSuccess) return (int)err;
+    ready[dev & 63] = true;
+    return 0;
+}
+
+PpoAdam make_adam(const acas2d_ppo_config &c)
+{
+    PpoAdam h;
+    h.lr = c.lr; h.beta1 = c.beta1; h.beta2 = c.beta2; h.eps = c.adam_eps; h.max_grad_norm = c.max_grad_norm;
+    return h;
+}
+
+int launch_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const float *obs, const float *actions,
+                    const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
+                    int64_t minibatch, float *workspace, int32_t *adam_step, cudaStream_t st)
+{
+    const int64_t tiles = (minibatch + kPpoTile - 1) / kPpoTile;
+    const int ctas = (int)(tiles < kPpoMaxCtas ? tiles : kPpoMaxCtas);
+    PpoBatch b;
+    b.obs = obs; b.actions = actions; b.old_logp = old_logp; b.adv = advantages; b.ret = returns;
+    b.idx = indices; b.mb = minibatch;
+    ppo_grad_kernel<<<dim3((unsigned)ctas, 2), kPpoThreads, kPpoSmemBytes, st>>>(
+        params, b, cfg->normalize_advantage, cfg->clip_range, cfg->vf_coef, workspace + ACAS2D_PPO_WORKSPACE_HEAD, adam_step);
+    return ctas;
+}
+}  // namespace
+
+int acas2d_ppo_prepare(void) { return ppo_prepare_device(); }
+
 int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const float *obs, const float *actions,
                     const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
                     int64_t minibatch, float *workspace, float *grad, float *loss_stats, int32_t *adam_step,
@@ -1047,41 +1087,49 @@ int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const flo
     if (minibatch <= 0) return ACAS2D_E_BAD_SIZE;
     if (!cfg || !params || !obs || !actions || !old_logp || !advantages || !returns || !workspace || !grad)
         return ACAS2D_E_NULL;
+    if (int e = ppo_prepare_device()) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpoSmemBytes);
-        if (err != cudaSuccess) return (int)err;
-        attr_set[dev & 63] = true;
-    }
-    float *adv_stats = workspace, *partials = workspace + 4;
-    int kernels = 2;
-    if (cfg->normalize_advantage) {
-        ppo_adv_stats_kernel<<<1, 1024, 0, st>>>(advantages, indices, minibatch, adv_stats);
-        ++kernels;
-    }
-    const int64_t tiles = (minibatch + kPpoTile - 1) / kPpoTile;
-    const int ctas = (int)(tiles < kPpoMaxCtas ? tiles : kPpoMaxCtas);
-    PpoBatch b;
-    b.obs = obs; b.actions = actions; b.old_logp = old_logp; b.adv = advantages; b.ret = returns;
-    b.idx = indices; b.mb = minibatch;
-    ppo_grad_kernel<<<dim3((unsigned)ctas, 2), kPpoThreads, kPpoSmemBytes, st>>>(
-        params, b, cfg->normalize_advantage ? adv_stats : nullptr, cfg->clip_range, cfg->vf_coef, partials);
-    ppo_reduce_kernel<<<(kPpoParams + 255) / 256, 256, 0, st>>>(partials, ctas, cfg->ent_coef, 1.0f / (float)minibatch,
-                                                                grad, loss_stats, adam_step);
-    return finish_launch(kernels);
+    const int ctas = launch_ppo_grad(cfg, params, obs, actions, old_logp, advantages, returns, indices, minibatch,
+                                     workspace, adam_step, st);
+    ppo_reduce_kernel<<<kPpoUpdateCtas, 256, 0, st>>>(workspace + ACAS2D_PPO_WORKSPACE_HEAD, ctas, cfg->ent_coef,
+                                                      1.0f / (float)minibatch, grad, loss_stats);
+    return finish_launch(2);
 }
 
 int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *grad, float grad_scale,
                     float *adam_m, float *adam_v, const int32_t *adam_step, float *loss_stats, void *stream)
 {
     if (!cfg || !params || !grad || !adam_m || !adam_v || !adam_step) return ACAS2D_E_NULL;
-    ppo_adam_kernel<<<(kPpoParams + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        params, grad, grad_scale, adam_m, adam_v, adam_step, cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps,
-        cfg->max_grad_norm, loss_stats);
+    if (int e = ppo_prepare_device()) return e;
+    ppo_adam_kernel<<<kPpoUpdateCtas, 256, 0, (cudaStream_t)stream>>>(
+        params, grad, grad_scale, adam_m, adam_v, adam_step, make_adam(*cfg), loss_stats);
     return finish_launch();
+}
+
+int acas2d_ppo_step(const acas2d_ppo_config *cfg, float *params, const float *obs, const float *actions,
+                    const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
+                    int64_t minibatch, float *workspace, float *adam_m, float *adam_v, int32_t *sync,
+                    float *loss_stats, float *grad_out, int32_t rank, int32_t world, void *const *peer_exchange,
+                    void *stream)
+{
+    if (minibatch <= 0 || world < 1 || world > kPpoMaxRanks || rank < 0 || rank >= world) return ACAS2D_E_BAD_SIZE;
+    if (!cfg || !params || !obs || !actions || !old_logp || !advantages || !returns || !workspace || !adam_m ||
+        !adam_v || !sync || (world > 1 && !peer_exchange))
+        return ACAS2D_E_NULL;
+    PpoPeers peers;
+    for (int r = 0; r < kPpoMaxRanks; ++r) peers.block[r] = nullptr;
+    for (int r = 0; r < world && world > 1; ++r) {
+        if (!peer_exchange[r]) return ACAS2D_E_NULL;
+        peers.block[r] = (float *)peer_exchange[r];
+    }
+    if (int e = ppo_prepare_device()) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = launch_ppo_grad(cfg, params, obs, actions, old_logp, advantages, returns, indices, minibatch,
+                                     workspace, sync, st);
+    ppo_update_kernel<<<kPpoUpdateCtas, 256, 0, st>>>(params, workspace + ACAS2D_PPO_WORKSPACE_HEAD, ctas, cfg->ent_coef,
+                                                      1.0f / (float)minibatch, workspace, peers, rank, world, adam_m, adam_v,
+                                                      sync, make_adam(*cfg), loss_stats, grad_out);
+    return finish_launch(2);
 }
 
 int64_t acas2d_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

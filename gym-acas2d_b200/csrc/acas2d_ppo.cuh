@@ -8,14 +8,19 @@
 // (ppo.py there), and the numerics reference in tests/ is the same loss written in plain torch float32
 // (gym_ACAS2D/ppo.py: reference_loss) differentiated by autograd.
 //
-// One gradient step = three small kernels (+ one optional all-reduce between the last two):
-//   ppo_adv_stats_kernel  mean / unbiased std of the minibatch's advantages (one CTA, two passes)
+// One gradient step = two kernels:
 //   ppo_grad_kernel       forward + backward of BOTH networks over the minibatch: grid (G, 2), blockIdx.y
 //                         picks actor or critic (their losses do not interact), each CTA walks 64-sample
 //                         tiles, everything in shared memory, weight gradients accumulated in registers
-//                         across its tiles, one partial-gradient row per CTA
-//   ppo_reduce_kernel     fixed-order sum of the partial rows -> grad[9612], loss statistics, Adam step count
-//   ppo_adam_kernel       global norm (recomputed per CTA, same order everywhere), clip, Adam
+//                         across its tiles, one partial-gradient row per CTA; the actor CTAs first take the
+//                         mean / unbiased std of the minibatch's advantages (two passes, every CTA the same)
+//   ppo_update_kernel     fixed-order sum of the partial rows, the data-parallel gradient exchange over
+//                         NVLink peer memory (each rank publishes its 38 KB gradient in a peer-mapped,
+//                         double-buffered block, signals its peers with release stores and sums all ranks'
+//                         blocks in rank order -- bit-identical on every rank), global norm, clip, Adam:
+//                         38 co-resident CTAs with a counter barrier between the phases
+// plus, for callers that exchange gradients themselves (torch.distributed all-reduce), the same work split
+// as ppo_grad_kernel -> ppo_reduce_kernel (-> all-reduce) -> ppo_adam_kernel.
 // The matrices are 64-wide: a minibatch step is ~0.1 GFLOP, launch/latency-bound, so this is float32 on
 // the CUDA cores (bit-comparable with the torch float32 reference) rather than TF32 tensor-core code.
 // Everything is deterministic: no floating-point atomics.
@@ -110,30 +115,9 @@ __device__ __forceinline__ double ppo_block_sum_d(double v, double *red)
     return s;
 }
 
-// stats[0] = mean, stats[1] = 1 / (std + 1e-8) of adv[idx[0..mb)], std with Bessel's correction
-// (SB3 ppo.py: advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)).
-__global__ void __launch_bounds__(1024)
-ppo_adv_stats_kernel(const float *__restrict__ adv, const int64_t *__restrict__ idx, const int64_t mb, float *stats)
-{
-    __shared__ double red[32];
-    double s = 0.0;
-    for (int64_t k = threadIdx.x; k < mb; k += blockDim.x) s += (double)adv[idx ? idx[k] : k];
-    const double mean = ppo_block_sum_d(s, red) / (double)mb;
-    double q = 0.0;
-    for (int64_t k = threadIdx.x; k < mb; k += blockDim.x) {
-        const double d = (double)adv[idx ? idx[k] : k] - mean;
-        q += d * d;
-    }
-    const double var = ppo_block_sum_d(q, red) / (double)(mb > 1 ? mb - 1 : 1);
-    if (threadIdx.x == 0) {
-        stats[0] = (float)mean;
-        stats[1] = 1.0f / ((float)sqrt(var) + 1e-8f);
-    }
-}
-
 __global__ void __launch_bounds__(kPpoThreads, 2)
-ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const float *__restrict__ adv_stats,
-                const float clip_range, const float vf_coef, float *__restrict__ partials)
+ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int normalize_advantage,
+                const float clip_range, const float vf_coef, float *__restrict__ partials, int32_t *adam_step)
 {
     extern __shared__ __align__(16) float sm[];
     float *sW2 = sm + kPpoSmW2, *sW2T = sm + kPpoSmW2T, *sW1 = sm + kPpoSmW1, *sb1 = sm + kPpoSmB1,
@@ -155,8 +139,26 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const float 
     const float b3 = w[kPolB3];
     const float log_std = params[kPpoLogStd];
     const float inv_var = __expf(-2.0f * log_std);
-    const float adv_mean = adv_stats ? adv_stats[0] : 0.0f, adv_scale = adv_stats ? adv_stats[1] : 1.0f;
     const float inv_mb = 1.0f / (float)b.mb;
+    if (adam_step && blockIdx.x == 0 && net == 0 && t == 0) *adam_step += 1;     // nobody reads it in this kernel
+
+    // SB3 ppo.py: advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8) over the minibatch
+    // (std with Bessel's correction).  Every actor CTA computes it itself, in the same order.
+    float adv_mean = 0.0f, adv_scale = 1.0f;
+    if (normalize_advantage && net == 0) {                                       // block-uniform
+        double *dred = (double *)sred;
+        double s = 0.0;
+        for (int64_t k = t; k < b.mb; k += kPpoThreads) s += (double)b.adv[b.idx ? b.idx[k] : k];
+        const double mean = ppo_block_sum_d(s, dred) / (double)b.mb;
+        double q = 0.0;
+        for (int64_t k = t; k < b.mb; k += kPpoThreads) {
+            const double d = (double)b.adv[b.idx ? b.idx[k] : k] - mean;
+            q += d * d;
+        }
+        const double var = ppo_block_sum_d(q, dred) / (double)(b.mb > 1 ? b.mb - 1 : 1);
+        adv_mean = (float)mean;
+        adv_scale = 1.0f / ((float)sqrt(var) + 1e-8f);
+    }
 
     // gradient accumulators, kept in registers across this CTA's tiles
     float gW2[4][4] = {};                    // dW2[4 jg + q][4 ig + r]   (jg = t >> 4, ig = t & 15)
@@ -348,33 +350,55 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const float 
     }
 }
 
-// grad[p] = sum over the CTAs' partial rows, in row order.  loss_stats: 0 policy loss, 1 value loss (MSE),
-// 2 approx KL, 3 clip fraction (SB3's logged quantities); 4 = gradient norm (written by ppo_adam_kernel).
+// Sum of the CTAs' partial rows for parameter p, in row order (deterministic).
+__device__ __forceinline__ float ppo_reduce_param(const float *__restrict__ partials, const int ctas, const int p,
+                                                  const float ent_coef)
+{
+    float s = 0.0f;
+    if (p < 2 * kPolFloats) {
+        const int net = p >= kPolFloats, q = p - net * kPolFloats;
+        const float *src = partials + (size_t)net * ctas * kPpoPartial + q;
+        for (int c = 0; c < ctas; ++c) s += src[(size_t)c * kPpoPartial];
+    } else if (p == kPpoLogStd) {
+        for (int c = 0; c < ctas; ++c) s += partials[(size_t)c * kPpoPartial + kPpoStatBase];
+        s -= ent_coef;                        // entropy of N(., sigma) = log_std + const; loss has -ent_coef * entropy
+    }
+    return s;
+}
+
+// loss_stats: 0 policy loss, 1 value loss (MSE), 2 approx KL, 3 clip fraction (SB3's logged quantities);
+// 4 = gradient norm before clipping.  Called by threads 1..4 of one CTA.
+__device__ __forceinline__ void ppo_write_loss_stat(const float *__restrict__ partials, const int ctas, const int f,
+                                                    const float inv_mb, float *__restrict__ loss_stats)
+{
+    const int net = (f == 2) ? 1 : 0;         // f: 1 pg / 2 value / 3 kl / 4 clip
+    float s = 0.0f;
+    for (int c = 0; c < ctas; ++c) s += partials[((size_t)net * ctas + c) * kPpoPartial + kPpoStatBase + f];
+    loss_stats[f - 1] = s * inv_mb;
+}
+
 __global__ void __launch_bounds__(256)
 ppo_reduce_kernel(const float *__restrict__ partials, const int ctas, const float ent_coef, const float inv_mb,
-                  float *__restrict__ grad, float *__restrict__ loss_stats, int32_t *adam_step)
+                  float *__restrict__ grad, float *__restrict__ loss_stats)
 {
     const int p = blockIdx.x * 256 + threadIdx.x;
-    if (p < kPpoParams) {
-        float s = 0.0f;
-        if (p < 2 * kPolFloats) {
-            const int net = p >= kPolFloats, q = p - net * kPolFloats;
-            const float *src = partials + (size_t)net * ctas * kPpoPartial + q;
-            for (int c = 0; c < ctas; ++c) s += src[(size_t)c * kPpoPartial];
-        } else if (p == kPpoLogStd) {
-            for (int c = 0; c < ctas; ++c) s += partials[(size_t)c * kPpoPartial + kPpoStatBase];
-            s -= ent_coef;                    // entropy of N(., sigma) = log_std + const; loss has -ent_coef * entropy
-        }
-        grad[p] = s;
-    }
-    if (blockIdx.x == 0 && threadIdx.x >= 1 && threadIdx.x <= 4 && loss_stats) {
-        const int f = threadIdx.x;            // pg / value / kl / clip
-        const int net = (f == 2) ? 1 : 0;
-        float s = 0.0f;
-        for (int c = 0; c < ctas; ++c) s += partials[((size_t)net * ctas + c) * kPpoPartial + kPpoStatBase + f];
-        loss_stats[f - 1] = s * inv_mb;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && adam_step) *adam_step += 1;
+    if (p < kPpoParams) grad[p] = ppo_reduce_param(partials, ctas, p, ent_coef);
+    if (blockIdx.x == 0 && threadIdx.x >= 1 && threadIdx.x <= 4 && loss_stats)
+        ppo_write_loss_stat(partials, ctas, threadIdx.x, inv_mb, loss_stats);
+}
+
+struct PpoAdam { float lr, beta1, beta2, eps, max_grad_norm; };
+
+// torch.optim.Adam(lr, betas, eps).step() for one parameter, g already clipped.
+__device__ __forceinline__ void ppo_adam_param(float *params, float *m, float *v, const int p, const float g,
+                                               const int step, const PpoAdam &h)
+{
+    const float mn = h.beta1 * m[p] + (1.0f - h.beta1) * g;
+    const float vn = h.beta2 * v[p] + (1.0f - h.beta2) * g * g;
+    m[p] = mn; v[p] = vn;
+    const float bc1 = 1.0f - powf(h.beta1, (float)step), bc2 = 1.0f - powf(h.beta2, (float)step);
+    const float denom = sqrtf(vn) / sqrtf(bc2) + h.eps;
+    params[p] -= (h.lr / bc1) * (mn / denom);
 }
 
 // torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.Adam(lr, betas, eps).step(), on
@@ -383,8 +407,7 @@ ppo_reduce_kernel(const float *__restrict__ partials, const int ctas, const floa
 __global__ void __launch_bounds__(256)
 ppo_adam_kernel(float *__restrict__ params, const float *__restrict__ grad, const float grad_scale,
                 float *__restrict__ m, float *__restrict__ v, const int32_t *__restrict__ adam_step,
-                const float lr, const float beta1, const float beta2, const float eps, const float max_grad_norm,
-                float *__restrict__ loss_stats)
+                const PpoAdam h, float *__restrict__ loss_stats)
 {
     __shared__ float red[8];
     float q = 0.0f;
@@ -393,19 +416,110 @@ ppo_adam_kernel(float *__restrict__ params, const float *__restrict__ grad, cons
         q = fmaf(g, g, q);
     }
     const float norm = sqrtf(ppo_block_sum(q, red));
-    float coef = (max_grad_norm > 0.0f) ? max_grad_norm / (norm + 1e-6f) : 1.0f;
+    float coef = (h.max_grad_norm > 0.0f) ? h.max_grad_norm / (norm + 1e-6f) : 1.0f;
     coef = fminf(coef, 1.0f);
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss_stats) loss_stats[4] = norm;
     const int p = blockIdx.x * 256 + threadIdx.x;
     if (p > kPpoLogStd) return;
-    const int step = *adam_step;
-    const float g = grad[p] * grad_scale * coef;
-    const float mn = beta1 * m[p] + (1.0f - beta1) * g;
-    const float vn = beta2 * v[p] + (1.0f - beta2) * g * g;
-    m[p] = mn; v[p] = vn;
-    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-    const float denom = sqrtf(vn) / sqrtf(bc2) + eps;
-    params[p] -= (lr / bc1) * (mn / denom);
+    ppo_adam_param(params, m, v, p, grad[p] * grad_scale * coef, *adam_step, h);
+}
+
+// ---------------------------------------------------------------- fused update (+ NVLink gradient exchange)
+constexpr int kPpoUpdateCtas = (kPpoParams + 255) / 256;          // 38: co-resident on any B200
+constexpr int kPpoMaxRanks = ACAS2D_PPO_MAX_RANKS;
+constexpr int kPpoXFlags = 2 * kPpoParams;                        // exchange block: grad[2][9612] | uint32 flags[16]
+
+struct PpoPeers { float *block[kPpoMaxRanks]; };                  // every rank's exchange block, peer-mapped
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Barrier over the CTAs of ONE launch (all co-resident: 38 CTAs): arrivals are counted on a monotonic
+// counter, `target` = arrivals expected once every CTA has reached this barrier instance (wrap-safe compare).
+__device__ __forceinline__ void ppo_grid_barrier(unsigned *counter, const unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while ((int)(ld_acquire_gpu_u32(counter) - target) < 0) {}
+    }
+    __syncthreads();
+}
+
+// sync: int32[4] = { Adam step (incremented by ppo_grad_kernel), barrier arrivals, spare, spare }.
+__global__ void __launch_bounds__(256)
+ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials, const int ctas, const float ent_coef,
+                  const float inv_mb, float *__restrict__ norm_parts, const PpoPeers peers, const int rank, const int world,
+                  float *__restrict__ m, float *__restrict__ v, int32_t *sync, const PpoAdam h,
+                  float *__restrict__ loss_stats, float *__restrict__ grad_out)
+{
+    __shared__ float red[8];
+    const int t = threadIdx.x, p = blockIdx.x * 256 + t;
+    const int step = sync[0];
+    unsigned *arrivals = (unsigned *)(sync + 1);
+    const unsigned barriers_per_step = world > 1 ? 2u : 1u;
+    const unsigned arrivals_before = gridDim.x * barriers_per_step * (unsigned)(step - 1);
+
+    // 1. this rank's gradient: fixed-order sum of the partial rows
+    float g = (p < kPpoParams) ? ppo_reduce_param(partials, ctas, p, ent_coef) : 0.0f;
+    if (blockIdx.x == 0 && t >= 1 && t <= 4 && loss_stats) ppo_write_loss_stat(partials, ctas, t, inv_mb, loss_stats);
+
+    // 2. data-parallel exchange over peer memory: publish, signal, wait, sum in rank order
+    if (world > 1) {
+        const int half = (step & 1) * kPpoParams;          // double-buffered: a fast rank's next step cannot overwrite
+        float *mine = peers.block[rank];                   // what a slow peer is still reading
+        if (p < kPpoParams) mine[half + p] = g;
+        __threadfence_system();
+        ppo_grid_barrier(arrivals, arrivals_before + gridDim.x);          // the whole gradient of this rank is published
+        if (blockIdx.x == 0 && t < world)
+            st_release_sys_u32((unsigned *)(peers.block[t] + kPpoXFlags) + rank, (unsigned)step);
+        if (t < world) {
+            const unsigned *flag = (const unsigned *)(mine + kPpoXFlags) + t;
+            while ((int)(ld_acquire_sys_u32(flag) - (unsigned)step) < 0) {}
+        }
+        __syncthreads();
+        if (p < kPpoParams) {
+            float s = 0.0f;
+            for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f32(peers.block[r] + half + p);
+            g = s * (1.0f / (float)world);
+        }
+    }
+    if (grad_out && p < kPpoParams) grad_out[p] = g;
+
+    // 3. global norm: one partial per CTA, barrier, every CTA sums the 38 partials in the same order
+    const float q = ppo_block_sum(g * g, red);
+    if (t == 0) norm_parts[blockIdx.x] = q;
+    ppo_grid_barrier(arrivals, arrivals_before + gridDim.x * barriers_per_step);
+    float total = 0.0f;
+    for (int c = 0; c < (int)gridDim.x; ++c) total += __ldcg(norm_parts + c);
+    const float norm = sqrtf(total);
+    float coef = (h.max_grad_norm > 0.0f) ? h.max_grad_norm / (norm + 1e-6f) : 1.0f;
+    coef = fminf(coef, 1.0f);
+    if (blockIdx.x == 0 && t == 0 && loss_stats) loss_stats[4] = norm;
+
+    // 4. Adam
+    if (p <= kPpoLogStd) ppo_adam_param(params, m, v, p, g * coef, step, h);
 }
 
 // Critic forward over n observation rows (the value head of SB3's MlpPolicy: mlp_extractor.value_net +

@@ -32,13 +32,16 @@ POLICY_FLOATS = 4804
 PPO_PARAM_FLOATS = 2 * POLICY_FLOATS + 4
 PPO_LOG_STD = 2 * POLICY_FLOATS
 PPO_PARTIAL_FLOATS, PPO_MAX_CTAS = 4816, 148
-PPO_WORKSPACE_FLOATS = 4 + 2 * PPO_MAX_CTAS * PPO_PARTIAL_FLOATS
+PPO_WORKSPACE_FLOATS = 64 + 2 * PPO_MAX_CTAS * PPO_PARTIAL_FLOATS
+PPO_MAX_RANKS = 16
+PPO_EXCHANGE_FLOATS = 2 * PPO_PARAM_FLOATS + PPO_MAX_RANKS
 PPO_LOSS_STATS = 8
 
 EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2d_step", "acas2d_step_host",
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
            "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render",
-           "acas2d_ppo_values", "acas2d_ppo_gae", "acas2d_ppo_grad", "acas2d_ppo_adam")
+           "acas2d_ppo_values", "acas2d_ppo_gae", "acas2d_ppo_grad", "acas2d_ppo_adam", "acas2d_ppo_step",
+           "acas2d_ppo_prepare")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -123,6 +126,9 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_ppo_gae.argtypes = [CP, vp, vp, vp, ctypes.c_int32, ctypes.c_int64, vp, vp, vp]
     lib.acas2d_ppo_grad.argtypes = [CP, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp]
     lib.acas2d_ppo_adam.argtypes = [CP, vp, vp, ctypes.c_float, vp, vp, vp, vp, vp]
+    lib.acas2d_ppo_step.argtypes = [CP, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp,
+                                    ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(vp), vp]
+    lib.acas2d_ppo_prepare.argtypes = []
     return lib
 
 

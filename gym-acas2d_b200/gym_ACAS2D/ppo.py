@@ -14,8 +14,11 @@ Two learners share the loss (``reference_loss``): ``FusedLearner`` -- this repo'
 ``acas2d_ppo_values / gae / grad / adam`` (``csrc/acas2d_ppo.cuh``), a whole epoch of gradient steps replayed
 as one CUDA graph -- and ``TorchLearner``, the plain torch float32 autograd version the kernels are checked
 against.  Under ``torchrun`` every rank owns a shard of the env batch (global env ids, so spawns do not
-depend on the GPU count), draws its minibatches from its own rollout and the ranks exchange one 38 KB
-gradient all-reduce per gradient step (NCCL) -- parameters stay bit-identical on all ranks.
+depend on the GPU count), draws its minibatches from its own rollout and the ranks average one 38 KB
+gradient per gradient step -- inside the update kernel itself, through NVLink peer memory
+(``exchange="p2p"``: symmetric-memory blocks, release/acquire flags, rank-ordered sum, no NCCL call, so the
+epoch graph also replays on N GPUs), or with an NCCL all-reduce between the gradient and the Adam kernels
+(``exchange="nccl"``).  Either way the parameters stay bit-identical on all ranks.
 """
 from __future__ import annotations
 
@@ -175,17 +178,19 @@ def _world():
 
 class FusedLearner:
     """PPO learner on this repo's kernels (``csrc/acas2d_ppo.cuh`` behind ``acas2d_ppo_*``): critic forward,
-    GAE, minibatch gradient of both networks, grad-norm clip + Adam -- float32, deterministic.  A whole epoch
-    (``minibatches`` gradient steps = 4 kernels each) is one CUDA-graph replay on a single GPU; with several
-    ranks each gradient step is grad -> NCCL all-reduce (38 KB) -> Adam."""
+    GAE, and per gradient step two kernels -- minibatch gradient of both networks, then reduction + gradient
+    exchange + grad-norm clip + Adam.  float32, deterministic.  A whole epoch (``minibatches`` gradient
+    steps) is one CUDA-graph replay, on one GPU and -- with the peer-memory exchange -- on N."""
 
     def __init__(self, device, cfg: Optional[PpoConfig] = None, init: Optional[Dict[str, torch.Tensor]] = None,
-                 cuda_graph: bool = True):
+                 cuda_graph: bool = True, exchange: str = "p2p"):
         dev = torch.device(device)
         if dev.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("FusedLearner runs on CUDA devices only; there is no CPU fallback (use TorchLearner)")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.device = dev
         self.lib = _native.load()
         self.cfg = cfg or PpoConfig.sb3_defaults()
@@ -194,11 +199,41 @@ class FusedLearner:
         self.adam_m, self.adam_v, self.grad = z(_native.PPO_PARAM_FLOATS), z(_native.PPO_PARAM_FLOATS), z(_native.PPO_PARAM_FLOATS)
         self.workspace = z(_native.PPO_WORKSPACE_FLOATS)
         self.loss_stats = z(_native.PPO_LOSS_STATS)
-        self.adam_step = z(1, dtype=torch.int32)
+        self.sync = z(4, dtype=torch.int32)              # [0] = Adam step count, [1] = barrier arrivals
+        self.adam_step = self.sync[0:1]
         self.cuda_graph = cuda_graph
+        self.rank, self.world = _world()
+        self.exchange = exchange if self.world > 1 else "none"
+        self._peer_ptrs = None
+        if self.exchange == "p2p":
+            self._open_peer_blocks()
+        with torch.cuda.device(dev):
+            _native.check(self.lib.acas2d_ppo_prepare(), "acas2d_ppo_prepare")
         self.launches = 0
         self._bound = None
         self._graph = None
+
+    def _open_peer_blocks(self) -> None:
+        """One exchange block per rank in symmetric memory (CUDA VMM, peer-mapped over NVLink): ``buffer_ptrs``
+        are every rank's block as seen from this process."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if self.world > _native.PPO_MAX_RANKS:
+            raise ValueError(f"the peer-memory exchange supports up to {_native.PPO_MAX_RANKS} ranks")
+        group = dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001  (newer torch enables every group implicitly)
+            pass
+        with torch.cuda.device(self.device):
+            self._xbuf = symm.empty(_native.PPO_EXCHANGE_FLOATS, dtype=torch.float32, device=self.device)
+            self._xbuf.zero_()
+            torch.cuda.synchronize(self.device)
+            self._xhdl = symm.rendezvous(self._xbuf, group)
+        ptrs = [int(x) for x in self._xhdl.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self._xbuf.data_ptr()
+        self._peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        dist.barrier()                                   # every block is zeroed before anyone signals
 
     # ---- plumbing
     def _stream(self):
@@ -240,29 +275,47 @@ class FusedLearner:
 
     # ---- gradient steps
     def gradient(self, obs, actions, old_logp, adv, ret, idx_ptr: Optional[int], mb: int) -> torch.Tensor:
-        """``grad`` <- gradient of the PPO loss over rows ``idx`` (device pointer to int64[mb]; None = first mb rows)."""
+        """``grad`` <- this rank's gradient of the PPO loss over rows ``idx`` (device pointer to int64[mb]; None =
+        first mb rows).  Two kernels (gradient, reduction); increments the Adam step count."""
         with torch.cuda.device(self.device):
             _native.check(self.lib.acas2d_ppo_grad(
                 self._c(), self.params.data_ptr(), obs.data_ptr(), actions.data_ptr(), old_logp.data_ptr(),
                 adv.data_ptr(), ret.data_ptr(), idx_ptr, int(mb), self.workspace.data_ptr(), self.grad.data_ptr(),
-                self.loss_stats.data_ptr(), self.adam_step.data_ptr(), self._stream()), "acas2d_ppo_grad")
-        self.launches += 3 if self.cfg.normalize_advantage else 2
+                self.loss_stats.data_ptr(), self.sync.data_ptr(), self._stream()), "acas2d_ppo_grad")
+        self.launches += 2
         return self.grad
 
     def apply(self, grad_scale: float = 1.0) -> None:
+        """Clip + Adam on ``grad * grad_scale`` (one kernel)."""
         with torch.cuda.device(self.device):
             _native.check(self.lib.acas2d_ppo_adam(self._c(), self.params.data_ptr(), self.grad.data_ptr(), float(grad_scale),
-                                                   self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.adam_step.data_ptr(),
+                                                   self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.sync.data_ptr(),
                                                    self.loss_stats.data_ptr(), self._stream()), "acas2d_ppo_adam")
         self.launches += 1
 
+    def step(self, obs, actions, old_logp, adv, ret, idx_ptr: Optional[int], mb: int, grad_out: bool = False) -> None:
+        """One whole gradient step: two kernels with the fused update (``exchange`` "none" / "p2p"), or gradient ->
+        NCCL all-reduce -> Adam (``exchange`` "nccl")."""
+        if self.exchange == "nccl":
+            self.gradient(obs, actions, old_logp, adv, ret, idx_ptr, mb)
+            self.apply(allreduce_gradient_(self.grad))
+            return
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.acas2d_ppo_step(
+                self._c(), self.params.data_ptr(), obs.data_ptr(), actions.data_ptr(), old_logp.data_ptr(),
+                adv.data_ptr(), ret.data_ptr(), idx_ptr, int(mb), self.workspace.data_ptr(), self.adam_m.data_ptr(),
+                self.adam_v.data_ptr(), self.sync.data_ptr(), self.loss_stats.data_ptr(),
+                self.grad.data_ptr() if grad_out else None, self.rank, self.world, self._peer_ptrs, self._stream()),
+                "acas2d_ppo_step")
+        self.launches += 2
+
     def _step(self, k: int) -> None:
         obs, act, logp, adv, ret, perm, mb = self._bound
-        self.gradient(obs, act, logp, adv, ret, perm.data_ptr() + 8 * k * mb, mb)
-        self.apply(allreduce_gradient_(self.grad))
+        self.step(obs, act, logp, adv, ret, perm.data_ptr() + 8 * k * mb, mb)
 
     def bind(self, obs, actions, old_logp, adv, ret, minibatches: int) -> None:
-        """Fix the (reused) flattened rollout storages the epochs read and capture one epoch as a CUDA graph."""
+        """Fix the (reused) flattened rollout storages the epochs read and capture one epoch as a CUDA graph
+        (not with the NCCL exchange: its all-reduces stay eager)."""
         n = actions.numel()
         for x in (obs, actions, old_logp, adv, ret):
             assert x.is_contiguous() and x.dtype == torch.float32 and x.device == self.device
@@ -270,12 +323,8 @@ class FusedLearner:
         self._bound = (obs, actions, old_logp, adv, ret, perm, n // minibatches)
         self.minibatches = minibatches
         self._graph = None
-        if self.cuda_graph and _world()[1] == 1:
-            saved = [x.clone() for x in (self.params, self.adam_m, self.adam_v, self.adam_step)]
-            self._step(0)                                     # loads the kernels / sets attributes outside capture
+        if self.cuda_graph and self.exchange != "nccl":
             torch.cuda.synchronize(self.device)
-            for dst, src in zip((self.params, self.adam_m, self.adam_v, self.adam_step), saved):
-                dst.copy_(src)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             graph = torch.cuda.CUDAGraph()
@@ -292,7 +341,7 @@ class FusedLearner:
         torch.randperm(perm.numel(), device=self.device, out=perm)
         if self._graph is not None:
             self._graph.replay()
-            self.launches += self.minibatches * (4 if self.cfg.normalize_advantage else 3)
+            self.launches += 2 * self.minibatches
         else:
             for k in range(self.minibatches):
                 self._step(k)
@@ -423,7 +472,7 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
           gamma: float = 0.99, gae_lambda: float = 0.95, clip_range: float = 0.2, n_epochs: int = 10,
           minibatches: int = 32, lr: float = 3e-4, vf_coef: float = 0.5, ent_coef: float = 0.0,
           max_grad_norm: float = 0.5, tensor_cores: bool = True, cuda_graph: bool = True, learner: str = "fused",
-          log=print) -> List[Dict[str, float]]:
+          exchange: str = "p2p", log=print) -> List[Dict[str, float]]:
     """Train from scratch; returns one record per iteration (episode statistics of that iteration's rollout
     over ALL ranks, timings).  ``num_envs`` is per rank; all tensors stay on ``device``.  ``learner``:
     "fused" = this repo's kernels, "torch" = the autograd reference."""
@@ -437,7 +486,10 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
     env = BatchedACAS2D(num_envs, device=dev, seed=seed, auto_reset=True, env_id_offset=rank * num_envs)
     env.reset()
     init = ActorCritic().sb3_state_dict()
-    L = (FusedLearner if learner == "fused" else TorchLearner)(dev, cfg, init, cuda_graph=cuda_graph)
+    if learner == "fused":
+        L = FusedLearner(dev, cfg, init, cuda_graph=cuda_graph, exchange=exchange)
+    else:
+        L = TorchLearner(dev, cfg, init, cuda_graph=cuda_graph)
     T, B = n_steps, num_envs
     n = T * B
     buffers = None
@@ -476,6 +528,14 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
                 "coll {collision_rate:.3f}  tout {timeout_rate:.3f}  len {mean_length:6.1f}  log_std {log_std:+.2f}  "
                 "rollout {rollout_s:.3f}s ({rollout_env_steps_per_s:.3g} steps/s)  learn {learn_s:.3f}s".format(**rec))
     train.last_policy = L
+    train.param_divergence = 0.0
+    if world > 1:                                              # the ranks must hold bit-identical parameters
+        import torch.distributed as dist
+        p0 = L.params.detach().clone()
+        dist.broadcast(p0, 0)
+        diff = (p0 - L.params.detach()).abs().max()
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        train.param_divergence = float(diff)
     return history
 
 
@@ -513,6 +573,8 @@ if __name__ == "__main__":
     ap.add_argument("--epochs", type=int, default=10)
     ap.add_argument("--learner", default="fused", choices=("fused", "torch"))
     ap.add_argument("--fp32", action="store_true", help="CUDA-core float32 actor instead of tcgen05 TF32")
+    ap.add_argument("--exchange", default="p2p", choices=("p2p", "nccl"),
+                    help="N > 1: gradient exchange inside the update kernel over NVLink peer memory, or an NCCL all-reduce")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -523,11 +585,13 @@ if __name__ == "__main__":
     dev = f"cuda:{torch.cuda.current_device()}"
     t_start = time.perf_counter()
     hist = train(a.envs, a.n_steps, a.iterations, device=dev, minibatches=a.minibatches, n_epochs=a.epochs,
-                 tensor_cores=not a.fp32, learner=a.learner)
+                 tensor_cores=not a.fp32, learner=a.learner, exchange=a.exchange)
     wall = time.perf_counter() - t_start
     if _world()[0] == 0:
         result = {"training": hist, "wall_s": wall, "world_size": world, "learner": a.learner,
+                  "param_divergence_over_ranks": train.param_divergence, "exchange": a.exchange if world > 1 else "none",
                   "rollout_s": sum(h["rollout_s"] for h in hist), "learn_s": sum(h["learn_s"] for h in hist)}
+        print(f"world {world}  parameter divergence over ranks {train.param_divergence}")
         print(f"wall {wall:.1f} s  (rollouts {result['rollout_s']:.2f} s, learner {result['learn_s']:.2f} s)")
         trained = MlpActor(train.last_policy.sb3_state_dict(), dev)
         result["eval_trained_here"] = evaluate(trained, device=dev)

@@ -226,7 +226,10 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
 #define ACAS2D_PPO_PARAM_FLOATS   (2 * ACAS2D_POLICY_FLOATS + 4)
 #define ACAS2D_PPO_PARTIAL_FLOATS 4816     /* one partial-gradient row */
 #define ACAS2D_PPO_MAX_CTAS       148      /* partial rows per network */
-#define ACAS2D_PPO_WORKSPACE_FLOATS (4 + 2 * ACAS2D_PPO_MAX_CTAS * ACAS2D_PPO_PARTIAL_FLOATS)
+#define ACAS2D_PPO_WORKSPACE_HEAD  64       /* per-CTA norm partials of the fused update */
+#define ACAS2D_PPO_WORKSPACE_FLOATS (ACAS2D_PPO_WORKSPACE_HEAD + 2 * ACAS2D_PPO_MAX_CTAS * ACAS2D_PPO_PARTIAL_FLOATS)
+#define ACAS2D_PPO_MAX_RANKS      16       /* data-parallel ranks of the peer-memory gradient exchange */
+#define ACAS2D_PPO_EXCHANGE_FLOATS (2 * ACAS2D_PPO_PARAM_FLOATS + ACAS2D_PPO_MAX_RANKS)
 #define ACAS2D_PPO_LOSS_STATS     8        /* policy loss, value loss, approx KL, clip fraction, grad norm, 3 spare */
 
 typedef struct acas2d_ppo_config {
@@ -251,7 +254,7 @@ int acas2d_ppo_gae(const acas2d_ppo_config *cfg, const float *rewards, const uin
  * (obs float[n][8], actions = unclipped samples, old_logp, advantages, returns: float[n]).
  * workspace float[ACAS2D_PPO_WORKSPACE_FLOATS]; grad float[ACAS2D_PPO_PARAM_FLOATS] (overwritten);
  * loss_stats float[ACAS2D_PPO_LOSS_STATS] or NULL; adam_step int32[1] or NULL, incremented by one.
- * Deterministic (no floating-point atomics).  Launches three kernels (two without normalisation). */
+ * Deterministic (no floating-point atomics).  Launches two kernels. */
 int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const float *obs, const float *actions,
                     const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
                     int64_t minibatch, float *workspace, float *grad, float *loss_stats, int32_t *adam_step,
@@ -262,6 +265,27 @@ int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const flo
  * adam_step = the counter acas2d_ppo_grad incremented.  loss_stats[4] receives the pre-clip norm. */
 int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *grad, float grad_scale,
                     float *adam_m, float *adam_v, const int32_t *adam_step, float *loss_stats, void *stream);
+
+/* One whole gradient step in two kernels: the gradient of acas2d_ppo_grad, then -- fused in one kernel --
+ * the fixed-order reduction, the data-parallel gradient exchange, clip_grad_norm_ and the Adam step.
+ * sync int32[4], zero-initialised, owned by the learner: [0] = Adam step count (incremented here).
+ * grad_out float[PARAM_FLOATS] or NULL: the (averaged) gradient that was applied, before clipping.
+ *
+ * world > 1 (one process per GPU, same call on every rank, same number of calls): peer_exchange is a HOST
+ * array of `world` DEVICE pointers, entry r = rank r's exchange block of ACAS2D_PPO_EXCHANGE_FLOATS floats
+ * (zero-initialised) mapped into this process (CUDA IPC / VMM symmetric memory; NVLink peer access).  Each
+ * rank publishes its gradient in its own block (double-buffered by step parity), signals every peer with a
+ * release store, waits for all peers' signals and sums the blocks in rank order -- every rank applies the
+ * bit-identical mean gradient and no NCCL call is made.  world == 1: rank 0, peer_exchange NULL. */
+int acas2d_ppo_step(const acas2d_ppo_config *cfg, float *params, const float *obs, const float *actions,
+                    const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
+                    int64_t minibatch, float *workspace, float *adam_m, float *adam_v, int32_t *sync,
+                    float *loss_stats, float *grad_out, int32_t rank, int32_t world, void *const *peer_exchange,
+                    void *stream);
+
+/* Sets the kernels' function attributes and loads them on the current device (optional; makes the first
+ * acas2d_ppo_* call legal inside a CUDA-graph capture). */
+int acas2d_ppo_prepare(void);
 
 /* Kernels launched by this library since load (all entry points). */
 int64_t acas2d_launch_count(void);

@@ -160,9 +160,12 @@ def test_fused_gradient_matches_torch_autograd(mb, normalize):
 
 
 @pytest.mark.gpu
-def test_fused_adam_steps_track_torch_adam():
+@pytest.mark.parametrize("path", ["split", "fused"])
+def test_fused_adam_steps_track_torch_adam(path):
     """40 clipped Adam steps on a fixed minibatch sequence: parameter blocks stay within 1e-4 of the torch
-    learner's (Adam's first steps move every parameter by ~lr regardless of gradient scale, so this is tight)."""
+    learner's (Adam's first steps move every parameter by ~lr regardless of gradient scale, so this is tight).
+    "split" = gradient / reduction kernels then the Adam kernel (the NCCL-exchange path), "fused" = the
+    two-kernel step with reduction + clip + Adam in one launch."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     dev = "cuda:0"
@@ -175,13 +178,19 @@ def test_fused_adam_steps_track_torch_adam():
     g = torch.Generator(device=dev).manual_seed(1)
     for step in range(40):
         idx = torch.randperm(n, device=dev, generator=g)[:mb].contiguous()
-        F.gradient(*data, idx.data_ptr(), mb)
-        F.apply(1.0)
-        T.gradient(*data, idx)
+        if path == "split":
+            F.gradient(*data, idx.data_ptr(), mb)
+            F.apply(1.0)
+        else:
+            F.step(*data, idx.data_ptr(), mb, grad_out=True)
+        ref_grad = T.gradient(*data, idx).detach().clone()
         T.apply(1.0)
         if step == 0:
-            norm_ref = float(T.params.grad.norm()) if cfg.max_grad_norm <= 0 else None
             assert F.logged()["grad_norm"] > cfg.max_grad_norm            # the clip is active in this test
+            assert abs(F.logged()["grad_norm"] - float(ref_grad.norm())) < 1e-4 * float(ref_grad.norm())
+        if path == "fused":
+            assert max(_group_errors(F.grad, ref_grad).values()) < 5e-4   # the gradient the fused kernel applied
+    assert int(F.adam_step) == 40
     err = float((F.params - T.params.detach()).abs().max())
     assert err < 1e-4, err
     assert float((F.params - ppo.pack_params(sd).to(dev)).abs().max()) > 5e-3     # and they did move
@@ -240,3 +249,56 @@ def test_ppo_training_loop_fused_learner():
     assert len(hist) == 2 and hist[1]["episodes"] > 0
     assert all(np.isfinite(v) for r in hist for v in r.values())
     assert abs(hist[1]["log_std"]) > 0.0 and hist[1]["grad_norm"] > 0.0
+
+
+@pytest.mark.gpu
+def test_peer_memory_gradient_exchange_two_gpus(tmp_path):
+    """BASELINE config 5 on N GPUs: the gradient exchange inside the update kernel (NVLink peer memory,
+    release/acquire flags, rank-ordered sum) against the NCCL all-reduce path, two ranks with different
+    minibatches: parameters bit-identical across ranks, both paths within 1e-6 of each other, and the captured
+    epoch graph replays across GPUs.  Needs two GPUs (skipped on a one-GPU box)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'gym-acas2d_b200')!r})
+        from gym_ACAS2D import ppo
+        from gym_ACAS2D.envs._native import PpoConfig
+        from tests.test_ppo_learner import synthetic_rollout, init_state_dict
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        cfg = PpoConfig.sb3_defaults()
+        n, minibatches = 4096, 8
+        data = synthetic_rollout(n, seed=100 + rank, device=dev)          # every rank its own rollout
+        out = {{}}
+        for exchange, graph in (("nccl", False), ("p2p", False), ("p2p", True)):
+            L = ppo.FusedLearner(dev, cfg, init_state_dict(), cuda_graph=graph, exchange=exchange)
+            L.bind(*data, minibatches)
+            torch.manual_seed(5)
+            for _ in range(3):
+                L.epoch()
+            torch.cuda.synchronize()
+            assert int(L.adam_step) == 3 * minibatches
+            p0 = L.params.clone()
+            dist.broadcast(p0, 0)
+            assert torch.equal(p0, L.params), f"ranks diverged with {{exchange}}"
+            out[(exchange, graph)] = L.params.clone()
+        assert torch.equal(out[("p2p", False)], out[("p2p", True)])
+        err = float((out[("p2p", True)] - out[("nccl", False)]).abs().max())
+        assert err < 1e-6, err
+        moved = float((out[("p2p", True)] - ppo.pack_params(init_state_dict()).to(dev)).abs().max())
+        assert moved > 1e-3
+        dist.barrier()
+        dist.destroy_process_group()
+        print("ok", rank, err)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29549", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
+    assert out.stdout.count("ok") == 2
