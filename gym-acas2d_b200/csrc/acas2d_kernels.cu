@@ -1126,7 +1126,7 @@ int acas2d_ppo_step(const acas2d_ppo_config *cfg, float *params, const float *ob
     cudaStream_t st = (cudaStream_t)stream;
     const int ctas = launch_ppo_grad(cfg, params, obs, actions, old_logp, advantages, returns, indices, minibatch,
                                      workspace, sync, st);
-    ppo_update_kernel<<<kPpoUpdateCtas, 256, 0, st>>>(params, workspace + ACAS2D_PPO_WORKSPACE_HEAD, ctas, cfg->ent_coef,
+    ppo_update_kernel<<<kPpoUpdateCtas, kPpoUpdateThreads, 0, st>>>(params, workspace + ACAS2D_PPO_WORKSPACE_HEAD, ctas, cfg->ent_coef,
                                                       1.0f / (float)minibatch, workspace, peers, rank, world, adam_m, adam_v,
                                                       sync, make_adam(*cfg), loss_stats, grad_out);
     return finish_launch(2);

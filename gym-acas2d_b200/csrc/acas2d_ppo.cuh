@@ -128,13 +128,21 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
     const float *w = params + net * kPolFloats;
     const int mg = t >> 4, ng = t & 15;                           // 16 x 16 thread grid of the 64 x 64 products
 
-    for (int e = t; e < 64 * 64; e += kPpoThreads) {              // W2[j][i], rows as SB3 stores them, and its transpose
-        const int j = e >> 6, i = e & 63;
-        const float v = w[kPolW2 + e];
-        sW2[j * kPpoLd + i] = v;
-        sW2T[i * kPpoLd + j] = v;
+    {   // W2[j][i], rows as SB3 stores them, and its transpose; W1: 128-bit loads, all in flight
+        float4 v2[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) v2[it] = ((const float4 *)(w + kPolW2))[t + kPpoThreads * it];
+        float4 v1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (t < 128) v1 = ((const float4 *)(w + kPolW1))[t];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int e = 4 * (t + kPpoThreads * it), j = e >> 6, i = e & 63;
+            *(float4 *)(sW2 + j * kPpoLd + i) = v2[it];
+            sW2T[(i + 0) * kPpoLd + j] = v2[it].x; sW2T[(i + 1) * kPpoLd + j] = v2[it].y;
+            sW2T[(i + 2) * kPpoLd + j] = v2[it].z; sW2T[(i + 3) * kPpoLd + j] = v2[it].w;
+        }
+        if (t < 128) *(float4 *)(sW1 + (t >> 1) * kPpoLdW1 + 4 * (t & 1)) = v1;
     }
-    for (int e = t; e < 64 * 8; e += kPpoThreads) sW1[(e >> 3) * kPpoLdW1 + (e & 7)] = w[kPolW1 + e];
     if (t < 64) { sb1[t] = w[kPolB1 + t]; sb2[t] = w[kPolB2 + t]; sw3[t] = w[kPolW3 + t]; }
     const float b3 = w[kPolB3];
     const float log_std = params[kPpoLogStd];
@@ -147,11 +155,25 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
     float adv_mean = 0.0f, adv_scale = 1.0f;
     if (normalize_advantage && net == 0) {                                       // block-uniform
         double *dred = (double *)sred;
+        constexpr int kKeep = 16;                          // minibatches up to 4096 rows are gathered exactly once
+        float a[kKeep];
+#pragma unroll
+        for (int u = 0; u < kKeep; ++u) {                  // all gathers (index, then value) in flight together
+            const int64_t k = u * kPpoThreads + t;
+            a[u] = (k < b.mb) ? b.adv[b.idx ? b.idx[k] : k] : 0.0f;
+        }
         double s = 0.0;
-        for (int64_t k = t; k < b.mb; k += kPpoThreads) s += (double)b.adv[b.idx ? b.idx[k] : k];
+#pragma unroll
+        for (int u = 0; u < kKeep; ++u) s += (double)a[u];
+        for (int64_t k = (int64_t)kKeep * kPpoThreads + t; k < b.mb; k += kPpoThreads) s += (double)b.adv[b.idx ? b.idx[k] : k];
         const double mean = ppo_block_sum_d(s, dred) / (double)b.mb;
         double q = 0.0;
-        for (int64_t k = t; k < b.mb; k += kPpoThreads) {
+#pragma unroll
+        for (int u = 0; u < kKeep; ++u) {
+            const double d = (double)a[u] - mean;
+            q += (u * kPpoThreads + t < b.mb) ? d * d : 0.0;
+        }
+        for (int64_t k = (int64_t)kKeep * kPpoThreads + t; k < b.mb; k += kPpoThreads) {
             const double d = (double)b.adv[b.idx ? b.idx[k] : k] - mean;
             q += d * d;
         }
@@ -187,7 +209,7 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb1[ng + 16 * r]);
+                    sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = acas_tanhf(acc[q][r] + sb1[ng + 16 * r]);
         }
         __syncthreads();
 
@@ -199,7 +221,7 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb2[ng + 16 * r]);
+                    sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = acas_tanhf(acc[q][r] + sb2[ng + 16 * r]);
         }
         __syncthreads();
 
@@ -342,39 +364,58 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
     }
     if (t < 64) { row[kPolB1 + t] = gb1; row[kPolB2 + t] = gb2; row[kPolW3 + t] = gw3; }
     if (t == 0) { row[kPolB3] = gb3; row[kPolB3 + 1] = 0.0f; row[kPolB3 + 2] = 0.0f; row[kPolB3 + 3] = 0.0f; }
-    const float s0 = ppo_block_sum(st_dls, sred), s1 = ppo_block_sum(st_pg, sred), s2 = ppo_block_sum(st_v, sred),
-                s3 = ppo_block_sum(st_kl, sred), s4 = ppo_block_sum(st_clip, sred);
-    if (t == 0) {
-        row[kPpoStatBase + 0] = s0; row[kPpoStatBase + 1] = s1; row[kPpoStatBase + 2] = s2;
-        row[kPpoStatBase + 3] = s3; row[kPpoStatBase + 4] = s4;
+    {   // the five per-sample statistics: warp shuffles, then lane 0 of every warp -> 8 x 5 words, summed in warp order
+        float st[5] = {st_dls, st_pg, st_v, st_kl, st_clip};
+#pragma unroll
+        for (int f = 0; f < 5; ++f)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) st[f] += __shfl_xor_sync(kFull, st[f], o);
+        if ((t & 31) == 0)
+#pragma unroll
+            for (int f = 0; f < 5; ++f) sred[(t >> 5) * 5 + f] = st[f];
+        __syncthreads();
+        if (t < 5) {
+            float v = 0.0f;
+            for (int wp = 0; wp < kPpoThreads / 32; ++wp) v += sred[wp * 5 + t];
+            row[kPpoStatBase + t] = v;
+        }
     }
 }
 
-// Sum of the CTAs' partial rows for parameter p, in row order (deterministic).
+// Sum of the CTAs' partial rows c = first, first + stride, ... for parameter p (fixed order; 8 loads in flight).
 __device__ __forceinline__ float ppo_reduce_param(const float *__restrict__ partials, const int ctas, const int p,
-                                                  const float ent_coef)
+                                                  const int first, const int stride)
 {
+    if (p > kPpoLogStd) return 0.0f;
+    const int net = (p < 2 * kPolFloats && p >= kPolFloats) ? 1 : 0;
+    const int q = (p == kPpoLogStd) ? kPpoStatBase : p - net * kPolFloats;
+    const float *src = partials + (size_t)net * ctas * kPpoPartial + q;
     float s = 0.0f;
-    if (p < 2 * kPolFloats) {
-        const int net = p >= kPolFloats, q = p - net * kPolFloats;
-        const float *src = partials + (size_t)net * ctas * kPpoPartial + q;
-        for (int c = 0; c < ctas; ++c) s += src[(size_t)c * kPpoPartial];
-    } else if (p == kPpoLogStd) {
-        for (int c = 0; c < ctas; ++c) s += partials[(size_t)c * kPpoPartial + kPpoStatBase];
-        s -= ent_coef;                        // entropy of N(., sigma) = log_std + const; loss has -ent_coef * entropy
+    for (int c0 = first; c0 < ctas; c0 += 8 * stride) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * stride;
+            a[u] = (c < ctas) ? __ldcg(src + (size_t)c * kPpoPartial) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += a[u];
     }
     return s;
 }
 
 // loss_stats: 0 policy loss, 1 value loss (MSE), 2 approx KL, 3 clip fraction (SB3's logged quantities);
-// 4 = gradient norm before clipping.  Called by threads 1..4 of one CTA.
+// 4 = gradient norm before clipping.  Called by all 32 lanes of one warp for statistic f = 1..4
+// (pg / value / kl / clip): lanes take rows lane, lane + 32, ...; xor-shuffle tree (fixed order).
 __device__ __forceinline__ void ppo_write_loss_stat(const float *__restrict__ partials, const int ctas, const int f,
                                                     const float inv_mb, float *__restrict__ loss_stats)
 {
-    const int net = (f == 2) ? 1 : 0;         // f: 1 pg / 2 value / 3 kl / 4 clip
+    const int net = (f == 2) ? 1 : 0, lane = threadIdx.x & 31;
     float s = 0.0f;
-    for (int c = 0; c < ctas; ++c) s += partials[((size_t)net * ctas + c) * kPpoPartial + kPpoStatBase + f];
-    loss_stats[f - 1] = s * inv_mb;
+    for (int c = lane; c < ctas; c += 32) s += __ldcg(partials + ((size_t)net * ctas + c) * kPpoPartial + kPpoStatBase + f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (lane == 0) loss_stats[f - 1] = s * inv_mb;
 }
 
 __global__ void __launch_bounds__(256)
@@ -382,9 +423,10 @@ ppo_reduce_kernel(const float *__restrict__ partials, const int ctas, const floa
                   float *__restrict__ grad, float *__restrict__ loss_stats)
 {
     const int p = blockIdx.x * 256 + threadIdx.x;
-    if (p < kPpoParams) grad[p] = ppo_reduce_param(partials, ctas, p, ent_coef);
-    if (blockIdx.x == 0 && threadIdx.x >= 1 && threadIdx.x <= 4 && loss_stats)
-        ppo_write_loss_stat(partials, ctas, threadIdx.x, inv_mb, loss_stats);
+    // entropy of N(., sigma) = log_std + const; the loss has -ent_coef * entropy
+    if (p < kPpoParams) grad[p] = ppo_reduce_param(partials, ctas, p, 0, 1) - (p == kPpoLogStd ? ent_coef : 0.0f);
+    if (blockIdx.x == 0 && threadIdx.x < 128 && loss_stats)
+        ppo_write_loss_stat(partials, ctas, 1 + (threadIdx.x >> 5), inv_mb, loss_stats);
 }
 
 struct PpoAdam { float lr, beta1, beta2, eps, max_grad_norm; };
@@ -468,28 +510,36 @@ __device__ __forceinline__ void ppo_grid_barrier(unsigned *counter, const unsign
 }
 
 // sync: int32[4] = { Adam step (incremented by ppo_grad_kernel), barrier arrivals, spare, spare }.
-__global__ void __launch_bounds__(256)
+// 1024 threads per CTA: four lanes share one parameter for the partial-row reduction (rows lane, lane + 4, ...).
+constexpr int kPpoUpdateThreads = 1024;
+
+__global__ void __launch_bounds__(kPpoUpdateThreads)
 ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials, const int ctas, const float ent_coef,
                   const float inv_mb, float *__restrict__ norm_parts, const PpoPeers peers, const int rank, const int world,
                   float *__restrict__ m, float *__restrict__ v, int32_t *sync, const PpoAdam h,
                   float *__restrict__ loss_stats, float *__restrict__ grad_out)
 {
-    __shared__ float red[8];
-    const int t = threadIdx.x, p = blockIdx.x * 256 + t;
+    __shared__ float red[32];
+    const int t = threadIdx.x, sub = t & 3, p = blockIdx.x * 256 + (t >> 2);
+    const bool owner = sub == 0 && p < kPpoParams;
     const int step = sync[0];
     unsigned *arrivals = (unsigned *)(sync + 1);
     const unsigned barriers_per_step = world > 1 ? 2u : 1u;
     const unsigned arrivals_before = gridDim.x * barriers_per_step * (unsigned)(step - 1);
 
-    // 1. this rank's gradient: fixed-order sum of the partial rows
-    float g = (p < kPpoParams) ? ppo_reduce_param(partials, ctas, p, ent_coef) : 0.0f;
-    if (blockIdx.x == 0 && t >= 1 && t <= 4 && loss_stats) ppo_write_loss_stat(partials, ctas, t, inv_mb, loss_stats);
+    // 1. this rank's gradient: fixed-order sum of the partial rows (all four lanes end with the same value)
+    float g = ppo_reduce_param(partials, ctas, p, sub, 4);
+    g += __shfl_xor_sync(kFull, g, 1);
+    g += __shfl_xor_sync(kFull, g, 2);
+    if (p == kPpoLogStd) g -= ent_coef;            // entropy of N(., sigma) = log_std + const; loss has -ent_coef * entropy
+    if (blockIdx.x == gridDim.x - 1 && t >= kPpoUpdateThreads - 128 && loss_stats)
+        ppo_write_loss_stat(partials, ctas, 1 + ((t >> 5) & 3), inv_mb, loss_stats);
 
     // 2. data-parallel exchange over peer memory: publish, signal, wait, sum in rank order
     if (world > 1) {
         const int half = (step & 1) * kPpoParams;          // double-buffered: a fast rank's next step cannot overwrite
         float *mine = peers.block[rank];                   // what a slow peer is still reading
-        if (p < kPpoParams) mine[half + p] = g;
+        if (owner) mine[half + p] = g;
         __threadfence_system();
         ppo_grid_barrier(arrivals, arrivals_before + gridDim.x);          // the whole gradient of this rank is published
         if (blockIdx.x == 0 && t < world)
@@ -499,27 +549,35 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
             while ((int)(ld_acquire_sys_u32(flag) - (unsigned)step) < 0) {}
         }
         __syncthreads();
-        if (p < kPpoParams) {
+        if (owner) {
             float s = 0.0f;
             for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f32(peers.block[r] + half + p);
             g = s * (1.0f / (float)world);
         }
     }
-    if (grad_out && p < kPpoParams) grad_out[p] = g;
+    if (grad_out && owner) grad_out[p] = g;
 
     // 3. global norm: one partial per CTA, barrier, every CTA sums the 38 partials in the same order
-    const float q = ppo_block_sum(g * g, red);
+    const float q = ppo_block_sum(owner ? g * g : 0.0f, red);
     if (t == 0) norm_parts[blockIdx.x] = q;
     ppo_grid_barrier(arrivals, arrivals_before + gridDim.x * barriers_per_step);
-    float total = 0.0f;
-    for (int c = 0; c < (int)gridDim.x; ++c) total += __ldcg(norm_parts + c);
+    if (t < 32) {                                          // 38 partials: lanes take c and c + 32, fixed shuffle tree
+        float x = 0.0f;
+        for (int c = t; c < (int)gridDim.x; c += 32) x += __ldcg(norm_parts + c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+        if (t == 0) red[0] = x;
+    }
+    __syncthreads();
+    const float total = red[0];
+    if (!owner || p > kPpoLogStd) return;
     const float norm = sqrtf(total);
     float coef = (h.max_grad_norm > 0.0f) ? h.max_grad_norm / (norm + 1e-6f) : 1.0f;
     coef = fminf(coef, 1.0f);
-    if (blockIdx.x == 0 && t == 0 && loss_stats) loss_stats[4] = norm;
+    if (p == 0 && loss_stats) loss_stats[4] = norm;
 
     // 4. Adam
-    if (p <= kPpoLogStd) ppo_adam_param(params, m, v, p, g * coef, step, h);
+    ppo_adam_param(params, m, v, p, g * coef, step, h);
 }
 
 // Critic forward over n observation rows (the value head of SB3's MlpPolicy: mlp_extractor.value_net +
@@ -556,7 +614,7 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb1[ng + 16 * r]);
+                    sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = acas_tanhf(acc[q][r] + sb1[ng + 16 * r]);
         }
         __syncthreads();
         {
@@ -566,7 +624,7 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = tanhf(acc[q][r] + sb2[ng + 16 * r]);
+                    sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = acas_tanhf(acc[q][r] + sb2[ng + 16 * r]);
         }
         __syncthreads();
         {
