@@ -1016,7 +1016,7 @@ int acas2d_ppo_values(const float *params, const float *obs, int64_t n, float *v
     }
     if (int e = ppo_prepare_device()) return e;
     long long grid = (long long)sms * 2;
-    const long long tiles = (n + kPpoTile - 1) / kPpoTile;
+    const long long tiles = (n + kPpoValTile - 1) / kPpoValTile;
     if (grid > tiles) grid = tiles;
     ppo_values_kernel<<<(unsigned)grid, kPpoThreads, kPpoValSmemBytes, (cudaStream_t)stream>>>(params, obs, n, values);
     return finish_launch();

@@ -35,7 +35,12 @@ constexpr int kPpoLogStd = 2 * kPolFloats;          // parameter block: actor | 
 constexpr int kPpoParams = ACAS2D_PPO_PARAM_FLOATS;
 constexpr int kPpoPartial = ACAS2D_PPO_PARTIAL_FLOATS;
 constexpr int kPpoMaxCtas = ACAS2D_PPO_MAX_CTAS;
-constexpr int kPpoTile = 64, kPpoThreads = 256;
+constexpr int kPpoTile = 32, kPpoThreads = 256;     // gradient kernel: 32-sample tiles -> two CTAs per SM (16 warps) at
+                                                    // a 4096-row minibatch; with 64-sample tiles one CTA per SM ran at
+                                                    // 12 % occupancy, every phase latency-bound (ncu: profiles/)
+constexpr int kPpoTq = kPpoTile / 16;               // sample rows per thread in the 16 x 16 thread grid
+constexpr int kPpoLps = kPpoThreads / kPpoTile;     // lanes per sample in the output-unit phase
+constexpr int kPpoValTile = 64;                     // critic-forward kernel: 64-row tiles
 constexpr int kPpoLd = 68;                          // shared-memory row stride of the 64-wide matrices (16-byte rows, bank-skewed)
 constexpr int kPpoLdW1 = 12;                        // same for W1 rows (8 wide)
 // partial row tail: dlog_std | sum pg term | sum value term | sum approx-kl term | clipped count
@@ -62,23 +67,23 @@ constexpr int kPpoSmemBytes = kPpoSmFloats * 4;
 
 #if defined(__CUDACC__)
 
-// acc[q][r] += sum_{k<K} A[(mg + 16 q) * lda + k] * B[(ng + 16 r) * ldb + k]: both operands are read as
+// acc[q][r] += sum_{k<K} A[(mg + 16 q) * lda + k] * B[(ng + 16 r) * ldb + k], q < TQ, r < 4: both operands are read as
 // 128-bit words along k.  Rows are dealt to the 16 x 16 thread grid interleaved (row = group + 16 q), so
 // the 8 threads of a quarter warp read 8 consecutive rows of B -- with a row stride of 68 (or 12) floats
 // those fall in 8 distinct 4-bank groups -- while A is a 2-address broadcast.
-template <int K>
+template <int K, int TQ>
 __device__ __forceinline__ void ppo_gemm_nt(const float *A, int lda, const float *B, int ldb, int mg, int ng,
-                                            float (&acc)[4][4])
+                                            float (&acc)[TQ][4])
 {
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
-        float4 a[4], b[4];
+        float4 a[TQ], b[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = *(const float4 *)(A + (mg + 16 * q) * lda + k);
+        for (int q = 0; q < TQ; ++q) a[q] = *(const float4 *)(A + (mg + 16 * q) * lda + k);
 #pragma unroll
         for (int r = 0; r < 4; ++r) b[r] = *(const float4 *)(B + (ng + 16 * r) * ldb + k);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < TQ; ++q)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 float s = acc[q][r];
@@ -203,10 +208,10 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
 
         // ---- layer 1: H1[s][j] = tanh(b1[j] + sum_c X[s][c] W1[j][c])
         {
-            float acc[4][4] = {};
-            ppo_gemm_nt<8>(sX, 8, sW1, kPpoLdW1, mg, ng, acc);
+            float acc[kPpoTq][4] = {};
+            ppo_gemm_nt<8, kPpoTq>(sX, 8, sW1, kPpoLdW1, mg, ng, acc);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kPpoTq; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
                     sH1[(mg + 16 * q) * kPpoLd + ng + 16 * r] = acas_tanhf(acc[q][r] + sb1[ng + 16 * r]);
@@ -215,24 +220,25 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
 
         // ---- layer 2: H2[s][j] = tanh(b2[j] + sum_i H1[s][i] W2[j][i])  -> sC
         {
-            float acc[4][4] = {};
-            ppo_gemm_nt<64>(sH1, kPpoLd, sW2, kPpoLd, mg, ng, acc);
+            float acc[kPpoTq][4] = {};
+            ppo_gemm_nt<64, kPpoTq>(sH1, kPpoLd, sW2, kPpoLd, mg, ng, acc);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kPpoTq; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
                     sC[(mg + 16 * q) * kPpoLd + ng + 16 * r] = acas_tanhf(acc[q][r] + sb2[ng + 16 * r]);
         }
         __syncthreads();
 
-        // ---- output unit and the loss derivative of each sample (4 lanes per sample)
+        // ---- output unit and the loss derivative of each sample (kPpoLps lanes per sample)
         {
-            const int s = t >> 2, part = t & 3;
+            constexpr int kJ = 64 / kPpoLps;
+            const int s = t / kPpoLps, part = t % kPpoLps;
             float y = 0.0f;
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) y = fmaf(sw3[part * 16 + jj], sC[s * kPpoLd + part * 16 + jj], y);
-            y += __shfl_xor_sync(kFull, y, 1);
-            y += __shfl_xor_sync(kFull, y, 2);
+            for (int jj = 0; jj < kJ; ++jj) y = fmaf(sw3[part * kJ + jj], sC[s * kPpoLd + part * kJ + jj], y);
+#pragma unroll
+            for (int o = 1; o < kPpoLps; o <<= 1) y += __shfl_xor_sync(kFull, y, o);
             y += b3;
             if (part == 0) {
                 const int64_t k = tile * kPpoTile + s;
@@ -268,13 +274,13 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
         }
         __syncthreads();
 
-        // ---- dw3, db3; dZ2 = dy * w3 * (1 - H2^2) in place of H2; db2 (column sums: 4 x 16 samples per unit)
+        // ---- dw3, db3; dZ2 = dy * w3 * (1 - H2^2) in place of H2; db2 (column sums: 4 x kPpoTile/4 samples per unit)
         {
             const int j = t & 63, part = t >> 6;
             const float w3j = sw3[j];
             float pw3 = 0.0f, pb2 = 0.0f;
 #pragma unroll 4
-            for (int s = part * 16; s < part * 16 + 16; ++s) {
+            for (int s = part * (kPpoTile / 4); s < (part + 1) * (kPpoTile / 4); ++s) {
                 const float h = sC[s * kPpoLd + j], dyv = sdy[s];
                 pw3 = fmaf(dyv, h, pw3);
                 const float dz = dyv * w3j * (1.0f - h * h);
@@ -291,7 +297,7 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
                    (sred[kPpoThreads + 128 + t] + sred[kPpoThreads + 192 + t]);
         }
         if (t < 32) {
-            float v = sdy[t] + sdy[t + 32];
+            float v = sdy[t] + (kPpoTile > 32 ? sdy[(t + 32) % kPpoTile] : 0.0f);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
             if (t == 0) gb3 += v;
@@ -319,10 +325,10 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
 
         // ---- dZ1[s][i] = (sum_j dZ2[s][j] W2[j][i]) * (1 - H1[s][i]^2), in place of H1
         {
-            float acc[4][4] = {};
-            ppo_gemm_nt<64>(sC, kPpoLd, sW2T, kPpoLd, mg, ng, acc);
+            float acc[kPpoTq][4] = {};
+            ppo_gemm_nt<64, kPpoTq>(sC, kPpoLd, sW2T, kPpoLd, mg, ng, acc);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kPpoTq; ++q)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     float *p = sH1 + (mg + 16 * q) * kPpoLd + ng + 16 * r;
@@ -337,7 +343,7 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
             const int j = t & 63, part = t >> 6;
             float pb1 = 0.0f;
 #pragma unroll 4
-            for (int s = part * 16; s < part * 16 + 16; ++s) pb1 += sH1[s * kPpoLd + j];
+            for (int s = part * (kPpoTile / 4); s < (part + 1) * (kPpoTile / 4); ++s) pb1 += sH1[s * kPpoLd + j];
             sred[t] = pb1;
             const int jw = t >> 2, c0 = 2 * (t & 3);
 #pragma unroll 4
@@ -515,7 +521,7 @@ constexpr int kPpoUpdateThreads = 1024;
 
 __global__ void __launch_bounds__(kPpoUpdateThreads)
 ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials, const int ctas, const float ent_coef,
-                  const float inv_mb, float *__restrict__ norm_parts, const PpoPeers peers, const int rank, const int world,
+                  const float inv_mb, float *__restrict__ norm_parts, const __grid_constant__ PpoPeers peers, const int rank, const int world,
                   float *__restrict__ m, float *__restrict__ v, int32_t *sync, const PpoAdam h,
                   float *__restrict__ loss_stats, float *__restrict__ grad_out)
 {
@@ -582,7 +588,7 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
 
 // Critic forward over n observation rows (the value head of SB3's MlpPolicy: mlp_extractor.value_net +
 // value_net): the forward half of ppo_grad_kernel, 64-row tiles, persistent CTAs.
-constexpr int kPpoValSmFloats = 64 * kPpoLd + 64 * kPpoLdW1 + 3 * 64 + kPpoTile * 8 + 2 * kPpoTile * kPpoLd;
+constexpr int kPpoValSmFloats = 64 * kPpoLd + 64 * kPpoLdW1 + 3 * 64 + kPpoValTile * 8 + 2 * kPpoValTile * kPpoLd;
 constexpr int kPpoValSmemBytes = kPpoValSmFloats * 4;
 
 __global__ void __launch_bounds__(kPpoThreads, 2)
@@ -590,7 +596,7 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
 {
     extern __shared__ __align__(16) float sm[];
     float *sW2 = sm, *sW1 = sW2 + 64 * kPpoLd, *sb1 = sW1 + 64 * kPpoLdW1, *sb2 = sb1 + 64, *sw3 = sb2 + 64,
-          *sX = sw3 + 64, *sH1 = sX + kPpoTile * 8, *sC = sH1 + kPpoTile * kPpoLd;
+          *sX = sw3 + 64, *sH1 = sX + kPpoValTile * 8, *sC = sH1 + kPpoValTile * kPpoLd;
     const int t = threadIdx.x, mg = t >> 4, ng = t & 15;
     const float *w = params + kPolFloats;
     for (int e = t; e < 64 * 64; e += kPpoThreads) sW2[(e >> 6) * kPpoLd + (e & 63)] = w[kPolW2 + e];
@@ -598,10 +604,10 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
     if (t < 64) { sb1[t] = w[kPolB1 + t]; sb2[t] = w[kPolB2 + t]; sw3[t] = w[kPolW3 + t]; }
     const float b3 = w[kPolB3];
     __syncthreads();
-    const int64_t ntiles = (n + kPpoTile - 1) / kPpoTile;
+    const int64_t ntiles = (n + kPpoValTile - 1) / kPpoValTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if (t < 2 * kPpoTile) {
-            const int64_t k = tile * kPpoTile + (t >> 1);
+        if (t < 2 * kPpoValTile) {
+            const int64_t k = tile * kPpoValTile + (t >> 1);
             float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (k < n) v = __ldcs((const float4 *)obs + 2 * k + (t & 1));
             *(float4 *)(sX + (t >> 1) * 8 + 4 * (t & 1)) = v;
@@ -609,7 +615,7 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
         __syncthreads();
         {
             float acc[4][4] = {};
-            ppo_gemm_nt<8>(sX, 8, sW1, kPpoLdW1, mg, ng, acc);
+            ppo_gemm_nt<8, 4>(sX, 8, sW1, kPpoLdW1, mg, ng, acc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -619,7 +625,7 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
         __syncthreads();
         {
             float acc[4][4] = {};
-            ppo_gemm_nt<64>(sH1, kPpoLd, sW2, kPpoLd, mg, ng, acc);
+            ppo_gemm_nt<64, 4>(sH1, kPpoLd, sW2, kPpoLd, mg, ng, acc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -634,7 +640,7 @@ ppo_values_kernel(const float *__restrict__ params, const float *__restrict__ ob
             for (int jj = 0; jj < 16; ++jj) y = fmaf(sw3[part * 16 + jj], sC[s * kPpoLd + part * 16 + jj], y);
             y += __shfl_xor_sync(kFull, y, 1);
             y += __shfl_xor_sync(kFull, y, 2);
-            const int64_t k = tile * kPpoTile + s;
+            const int64_t k = tile * kPpoValTile + s;
             if (part == 0 && k < n) values[k] = y + b3;
         }
         __syncthreads();
