@@ -114,8 +114,6 @@ inline DevParams make_dev_params(const acas2d_params &p)
     d.n_traffic = p.n_traffic;
     d.max_steps = (int32_t)p.max_steps;
     d.auto_reset = p.auto_reset;
-    d.uniform_speed = (p.airspeed_factor_min == p.airspeed_factor_max &&
-                       p.airspeed_factor_min == 1.0) ? 1 : 0;
     return d;
 }
 
@@ -194,10 +192,13 @@ ACAS_HD bool traffic_store(const StatePtrs &S, int64_t ij, const TrafficRec &t, 
 ACAS_HD Intruder intruder_at(const DevParams &P, const TrafficRec &t, double k)
 {
     Intruder it;
-    heading_to_velocity(P, t.v, t.psi, &it.dx, &it.dy);
+    double s, c;
+    sincos_deg(t.psi, &s, &c);
+    it.dx = (t.v * c) * P.dt;                                           // aircraft.py:25-26 with a_lat = 0
+    it.dy = (t.v * s) * P.dt;
     it.x = t.x0 + k * it.dx;
     it.y = t.y0 + k * it.dy;
-    it.vratio = P.uniform_speed ? 1.0 : P.airspeed / t.v;              // Q3
+    it.dyq = (P.airspeed * s) * P.dt;                                   // Q3 (no division: the player's speed times the sine)
     return it;
 }
 

@@ -69,7 +69,7 @@ struct DevParams {
     float reward_goal, reward_collision;
     float tn_x_span_f, tn_y_span_f, factor_min_f, factor_span_f, airspeed_f;   // float32 spawn of intruders n>0
     // ---- integers
-    int32_t n_traffic, max_steps, auto_reset, uniform_speed;
+    int32_t n_traffic, max_steps, auto_reset, pad_;
 };
 
 // forward: used by sincos_deg below
@@ -166,6 +166,8 @@ ACAS_HD int acas_rint_i(double x)
 // no local memory: ~30 FP64 instructions instead of ~55 for sincos().
 ACAS_HD void sincos_deg(double deg, double *s, double *c)
 {
+    // (the coefficients stay 64-bit immediates: moved to the constant bank, ptxas copies them into vector
+    //  registers every iteration -- as many instructions, plus a spill in the tiled kernel)
     const int q = acas_rint_i(deg * (1.0 / 90.0));
     const double r = fma((double)q, -90.0, deg);            // exact
     const double t = r * kDeg2Rad;
@@ -248,7 +250,8 @@ struct Player {
 struct Intruder {
     double x, y;        // CURRENT position
     double dx, dy;      // displacement per step (v cos psi dt, v sin psi dt)
-    double vratio;      // player speed / intruder speed (Q3; 1 when speeds are uniform)
+    double dyq;         // Q3: the reference's closing-speed look-ahead multiplies the INTRUDER's sine by the PLAYER's speed
+                        // (kinematics.py:71-73): airspeed * sin(psi) * dt; equals dy when the speeds are equal
 };
 
 // aircraft.py:16-26 for the player: heading += a_lat/v degrees (Q1), wrap, move one step.
@@ -300,7 +303,7 @@ ACAS_HD Encounter encounter(const DevParams &P, const Player &p, const Intruder 
     const double ex = p.cl * P.v_dt - t.dx;
     const double qx = ex - rx;
     const double qy = (p.sl * P.v_dt - t.dy) - ry;
-    const double ey = p.sl * P.v_dt - t.dy * t.vratio;
+    const double ey = p.sl * P.v_dt - t.dyq;
     const double q2 = qx * qx + qy * qy;
     const double dot = ex * qx + ey * qy;
 
