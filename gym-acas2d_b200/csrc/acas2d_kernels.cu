@@ -330,9 +330,19 @@ inline size_t tiled_warp_bytes(int N, int G)
 
 inline size_t tiled_smem_bytes(int N, int G) { return kTiledWarps * tiled_warp_bytes(N, G); }
 
+// Occupancy beats per-lane interleaving here (measured, frac of the HBM roofline at N = 2 / 8 / 16 / 32 / 64 / 128):
+//   5 blocks/SM (96 regs), unroll 2:  0.57 / 0.67 / 0.59 / 0.56 / 0.46 / 0.31
+//   6 blocks/SM (80 regs), unroll 1:  0.64 / 0.71 / 0.64 / 0.61 / 0.50 / 0.33
+//   7 blocks/SM (72 regs), unroll 1:  0.67 / 0.71 / 0.66 / 0.63 / 0.52 / 0.33     <- default
+//   8 blocks/SM (64 regs, spills):    0.67 / 0.68 / 0.64 / 0.62 / 0.50 / 0.33
 #ifndef ACAS2D_TILED_MIN_BLOCKS
-#define ACAS2D_TILED_MIN_BLOCKS 5
+#define ACAS2D_TILED_MIN_BLOCKS 7
 #endif
+#ifndef ACAS2D_TILED_UNROLL
+#define ACAS2D_TILED_UNROLL 1       /* intruders interleaved per lane (experiment switch) */
+#endif
+#define ACAS_PRAGMA(x) _Pragma(#x)
+#define ACAS_UNROLL(n) ACAS_PRAGMA(unroll n)
 template <int G, bool MINSEP>
 __global__ void __launch_bounds__(kTiledWarps * 32, ACAS2D_TILED_MIN_BLOCKS)
 step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
@@ -398,7 +408,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         const Float4 *trow = tile + e * TS;
         const double kd = (double)k;
         const bool any_residual = __any_sync(kFull, residual);      // injected float64 states only: keep it a branch
-#pragma unroll 2
+ACAS_UNROLL(ACAS2D_TILED_UNROLL)
         for (int m = 0; m < per_lane; ++m) {
             const Float4 h = trow[j];
             TrafficRec tr;

@@ -15,7 +15,7 @@ from typing import Optional
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # gym-acas2d_b200/
 CSRC_DIR = os.path.join(_PKG_ROOT, "csrc")
 REPO_ROOT = os.path.dirname(_PKG_ROOT)
-LIB_PATH = os.path.join(CSRC_DIR, "libacas2d_b200.so")
+LIB_PATH = os.environ.get("ACAS2D_LIB") or os.path.join(CSRC_DIR, "libacas2d_b200.so")   # ACAS2D_LIB: experiment builds
 SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh", "acas2d_policy_tc.cuh", "acas2d_dev.cuh", "acas2d_ppo.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
