@@ -240,6 +240,7 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line, nothing else
         dist.init_process_group("nccl", device_id=dev)
 
     N = args.n_traffic
