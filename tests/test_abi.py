@@ -66,6 +66,20 @@ def test_argument_errors_do_not_touch_the_device(lib):
     assert lib.acas2d_reset(ctypes.byref(p), ctypes.byref(s), None, None, None) == -3
     p.n_traffic = 0
     assert lib.acas2d_extract_state(ctypes.byref(p), ctypes.byref(s), None, None, None, None, None) == -2
+    # PPO learner entry points: same conventions
+    c = _native.PpoConfig.sb3_defaults()
+    assert (c.gamma, c.clip_range, c.normalize_advantage) == (ctypes.c_float(0.99).value, ctypes.c_float(0.2).value, 1)
+    assert lib.acas2d_ppo_values(None, None, 16, None, None) == -1
+    assert lib.acas2d_ppo_values(None, None, 0, None, None) == 0 and lib.acas2d_ppo_values(None, None, -1, None, None) == -3
+    assert lib.acas2d_ppo_gae(ctypes.byref(c), None, None, None, 8, 8, None, None, None) == -1
+    assert lib.acas2d_ppo_gae(ctypes.byref(c), None, None, None, -1, 8, None, None, None) == -3
+    assert lib.acas2d_ppo_grad(ctypes.byref(c), None, None, None, None, None, None, None, 64, None, None, None, None, None) == -1
+    assert lib.acas2d_ppo_grad(ctypes.byref(c), None, None, None, None, None, None, None, 0, None, None, None, None, None) == -3
+    assert lib.acas2d_ppo_adam(ctypes.byref(c), None, None, 1.0, None, None, None, None, None) == -1
+    step_args = [ctypes.byref(c)] + [None] * 7 + [64] + [None] * 6
+    assert lib.acas2d_ppo_step(*step_args, 0, 1, None, None) == -1
+    assert lib.acas2d_ppo_step(*step_args, 3, 2, None, None) == -3                      # rank outside the world
+    assert lib.acas2d_ppo_step(*step_args, 0, _native.PPO_MAX_RANKS + 1, None, None) == -3
     assert lib.acas2d_launch_count() == 0
 
 

@@ -166,13 +166,15 @@ def test_collect_rollout_buffers_are_consistent():
 
 @pytest.mark.gpu
 def test_ppo_training_loop_mechanics():
-    """Two tiny PPO iterations (rollout collection with the fused kernels + torch learner): finite
-    numbers, episodes finish, parameters move.  The full learning curve (100 % goal after 70 iterations
-    of 1024 envs x 1024 steps) is recorded in profiles/r01_ppo_training_curve.json."""
+    """Two tiny PPO iterations (rollout collection with the fused kernels + the torch autograd learner, i.e.
+    the numerics reference of the learner kernels, end to end): finite numbers, episodes finish, parameters
+    move.  The same loop on the learner kernels: tests/test_ppo_learner.py.  Full learning curves (100 % goal
+    after 70 iterations of 1024 envs x 1024 steps): profiles/r01_ppo_training_curve*.json."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from gym_ACAS2D import ppo
-    hist = ppo.train(num_envs=512, n_steps=600, iterations=2, minibatches=8, n_epochs=2, tensor_cores=True, log=None)
+    hist = ppo.train(num_envs=512, n_steps=600, iterations=2, minibatches=8, n_epochs=2, tensor_cores=True,
+                     learner="torch", log=None)
     assert len(hist) == 2 and hist[1]["episodes"] > 0
     assert all(np.isfinite(v) for r in hist for v in r.values())
     assert hist[1]["env_steps"] == 2 * 512 * 600
