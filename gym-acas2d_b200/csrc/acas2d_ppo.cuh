@@ -504,11 +504,14 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float *p)
 
 // Barrier over the CTAs of ONE launch (all co-resident: 38 CTAs): arrivals are counted on a monotonic
 // counter, `target` = arrivals expected once every CTA has reached this barrier instance (wrap-safe compare).
+// SYSTEM: the fence that publishes this CTA's stores (ordered before it by the bar.sync) is system-scope, so
+// that a peer GPU which later observes this rank's release flag also observes them.
+template <bool SYSTEM = false>
 __device__ __forceinline__ void ppo_grid_barrier(unsigned *counter, const unsigned target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (SYSTEM) __threadfence_system(); else __threadfence();
         atomicAdd(counter, 1u);
         while ((int)(ld_acquire_gpu_u32(counter) - target) < 0) {}
     }
@@ -546,8 +549,7 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
         const int half = (step & 1) * kPpoParams;          // double-buffered: a fast rank's next step cannot overwrite
         float *mine = peers.block[rank];                   // what a slow peer is still reading
         if (owner) mine[half + p] = g;
-        __threadfence_system();
-        ppo_grid_barrier(arrivals, arrivals_before + gridDim.x);          // the whole gradient of this rank is published
+        ppo_grid_barrier<true>(arrivals, arrivals_before + gridDim.x);    // the whole gradient of this rank is published
         if (blockIdx.x == 0 && t < world)
             st_release_sys_u32((unsigned *)(peers.block[t] + kPpoXFlags) + rank, (unsigned)step);
         if (t < world) {
@@ -556,8 +558,13 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
         }
         __syncthreads();
         if (owner) {
+            float a[kPpoMaxRanks];                         // all ranks' words in flight at once (one NVLink round trip),
+#pragma unroll
+            for (int r = 0; r < kPpoMaxRanks; ++r)         // then summed in rank order
+                a[r] = (r < world) ? ld_relaxed_sys_f32(peers.block[r] + half + p) : 0.0f;
             float s = 0.0f;
-            for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f32(peers.block[r] + half + p);
+#pragma unroll
+            for (int r = 0; r < kPpoMaxRanks; ++r) s += a[r];
             g = s * (1.0f / (float)world);
         }
     }
