@@ -502,24 +502,34 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float *p)
     return v;
 }
 
-// Barrier over the CTAs of ONE launch (all co-resident: 38 CTAs): arrivals are counted on a monotonic
-// counter, `target` = arrivals expected once every CTA has reached this barrier instance (wrap-safe compare).
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Barrier over the CTAs of ONE launch (all co-resident: 38 CTAs): arrivals are counted on a monotonic 64-bit
+// counter, `target` = arrivals expected once every CTA has reached this barrier instance.
 // SYSTEM: the fence that publishes this CTA's stores (ordered before it by the bar.sync) is system-scope, so
 // that a peer GPU which later observes this rank's release flag also observes them.
 template <bool SYSTEM = false>
-__device__ __forceinline__ void ppo_grid_barrier(unsigned *counter, const unsigned target)
+__device__ __forceinline__ void ppo_grid_barrier(unsigned long long *counter, const unsigned long long target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         if (SYSTEM) __threadfence_system(); else __threadfence();
-        atomicAdd(counter, 1u);
-        while ((int)(ld_acquire_gpu_u32(counter) - target) < 0) {}
+        atomicAdd(counter, 1ull);
+        while (ld_acquire_gpu_u64(counter) < target) {}
     }
     __syncthreads();
 }
 
-// sync: int32[4] = { Adam step (incremented by ppo_grad_kernel), barrier arrivals, spare, spare }.
-// 1024 threads per CTA: four lanes share one parameter for the partial-row reduction (rows lane, lane + 4, ...).
+// sync: int32[4] = { Adam step (incremented by ppo_grad_kernel), spare, 64-bit barrier-arrival counter }.  The
+// counter is only ever advanced by this kernel, by exactly gridDim.x * barriers_per_step per launch, so its value
+// at launch (rounded down: early CTAs of the same launch may already have arrived) numbers the launch -- the
+// barrier targets, the exchange-buffer parity and the peer flags all derive from that sequence number, not from
+// the Adam step count, and stay consistent whatever else the caller does with `sync[0]`.
 constexpr int kPpoUpdateThreads = 1024;
 
 __global__ void __launch_bounds__(kPpoUpdateThreads)
@@ -529,12 +539,16 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
                   float *__restrict__ loss_stats, float *__restrict__ grad_out)
 {
     __shared__ float red[32];
+    __shared__ unsigned long long s_before;
     const int t = threadIdx.x, sub = t & 3, p = blockIdx.x * 256 + (t >> 2);
     const bool owner = sub == 0 && p < kPpoParams;
     const int step = sync[0];
-    unsigned *arrivals = (unsigned *)(sync + 1);
-    const unsigned barriers_per_step = world > 1 ? 2u : 1u;
-    const unsigned arrivals_before = gridDim.x * barriers_per_step * (unsigned)(step - 1);
+    unsigned long long *arrivals = (unsigned long long *)(sync + 2);
+    const unsigned per_launch = gridDim.x * (world > 1 ? 2u : 1u);
+    if (t == 0) s_before = (ld_acquire_gpu_u64(arrivals) / per_launch) * per_launch;
+    __syncthreads();
+    const unsigned long long arrivals_before = s_before;
+    const unsigned seq = (unsigned)(arrivals_before / per_launch) + 1u;       // 1, 2, ...: this launch's number
 
     // 1. this rank's gradient: fixed-order sum of the partial rows (all four lanes end with the same value)
     float g = ppo_reduce_param(partials, ctas, p, sub, 4);
@@ -546,15 +560,15 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
 
     // 2. data-parallel exchange over peer memory: publish, signal, wait, sum in rank order
     if (world > 1) {
-        const int half = (step & 1) * kPpoParams;          // double-buffered: a fast rank's next step cannot overwrite
+        const int half = (int)(seq & 1u) * kPpoParams;      // double-buffered: a fast rank's next step cannot overwrite
         float *mine = peers.block[rank];                   // what a slow peer is still reading
         if (owner) mine[half + p] = g;
         ppo_grid_barrier<true>(arrivals, arrivals_before + gridDim.x);    // the whole gradient of this rank is published
         if (blockIdx.x == 0 && t < world)
-            st_release_sys_u32((unsigned *)(peers.block[t] + kPpoXFlags) + rank, (unsigned)step);
+            st_release_sys_u32((unsigned *)(peers.block[t] + kPpoXFlags) + rank, seq);
         if (t < world) {
             const unsigned *flag = (const unsigned *)(mine + kPpoXFlags) + t;
-            while ((int)(ld_acquire_sys_u32(flag) - (unsigned)step) < 0) {}
+            while ((int)(ld_acquire_sys_u32(flag) - seq) < 0) {}
         }
         __syncthreads();
         if (owner) {
@@ -573,7 +587,7 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
     // 3. global norm: one partial per CTA, barrier, every CTA sums the 38 partials in the same order
     const float q = ppo_block_sum(owner ? g * g : 0.0f, red);
     if (t == 0) norm_parts[blockIdx.x] = q;
-    ppo_grid_barrier(arrivals, arrivals_before + gridDim.x * barriers_per_step);
+    ppo_grid_barrier(arrivals, arrivals_before + per_launch);
     if (t < 32) {                                          // 38 partials: lanes take c and c + 32, fixed shuffle tree
         float x = 0.0f;
         for (int c = t; c < (int)gridDim.x; c += 32) x += __ldcg(norm_parts + c);

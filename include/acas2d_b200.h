@@ -268,7 +268,10 @@ int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *gr
 
 /* One whole gradient step in two kernels: the gradient of acas2d_ppo_grad, then -- fused in one kernel --
  * the fixed-order reduction, the data-parallel gradient exchange, clip_grad_norm_ and the Adam step.
- * sync int32[4], zero-initialised, owned by the learner: [0] = Adam step count (incremented here).
+ * sync int32[4] (16-byte aligned), zero-initialised, owned by the learner: [0] = Adam step count (incremented
+ * here), [2..3] = a 64-bit count of barrier arrivals that numbers the launches of the update kernel (its grid
+ * barriers, the exchange-buffer parity and the peer flags derive from it, not from the step count, so this call
+ * may be mixed with acas2d_ppo_grad / acas2d_ppo_adam on the same learner).
  * grad_out float[PARAM_FLOATS] or NULL: the (averaged) gradient that was applied, before clipping.
  *
  * world > 1 (one process per GPU, same call on every rank, same number of calls): peer_exchange is a HOST
