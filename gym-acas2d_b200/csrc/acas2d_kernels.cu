@@ -580,10 +580,16 @@ ACAS_UNROLL(ACAS2D_TILED_UNROLL)
     tally_flush_warp(S.stats, tally);
 }
 
+#ifndef ACAS2D_TILED_PER_LANE
+#define ACAS2D_TILED_PER_LANE 8     /* intruders per lane the group size aims at (experiment switch).  Measured frac at
+                                       N = 8 / 16 / 32 / 64: 2 per lane 0.43 / 0.38 / 0.36 / 0.30, 4: 0.60 / 0.53 / 0.50 / 0.42,
+                                       8: 0.71 / 0.66 / 0.63 / 0.52, 16: 0.70 / 0.51 / 0.49 / 0.40 -- the player update is redone
+                                       by every lane of a group, so small groups win until a lane's loop gets too long */
+#endif
 inline int tiled_group(int N)
 {
     int want = 1;
-    while (want < 32 && want * 8 < N) want <<= 1;        // about eight intruders per lane
+    while (want < 32 && want * ACAS2D_TILED_PER_LANE < N) want <<= 1;        // about eight intruders per lane
     int g = 1;
     while (g < want && N % (g * 2) == 0) g <<= 1;         // G must divide N
     return g;
