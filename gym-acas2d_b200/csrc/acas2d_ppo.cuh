@@ -133,6 +133,28 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
     const float *w = params + net * kPolFloats;
     const int mg = t >> 4, ng = t & 15;                           // 16 x 16 thread grid of the 64 x 64 products
 
+    // Gathers run one tile ahead of the arithmetic (and the first tile's ahead of the weight staging and the
+    // advantage statistics): observation-row halves by threads 0 .. 2 * tile - 1, the per-sample scalars by lane 0
+    // of each sample's lane group.  index -> row is two dependent trips to L2 / HBM otherwise on the critical path.
+    float4 pre_obs = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float pre_act = 0.0f, pre_logp = 0.0f, pre_adv = 0.0f, pre_ret = 0.0f;
+    auto prefetch = [&](const int64_t tile) {
+        if (t < 2 * kPpoTile) {
+            const int64_t k = tile * kPpoTile + (t >> 1);
+            pre_obs = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (k < b.mb) pre_obs = ((const float4 *)b.obs)[2 * (b.idx ? b.idx[k] : k) + (t & 1)];
+        }
+        if (t % kPpoLps == 0) {
+            const int64_t k = tile * kPpoTile + t / kPpoLps;
+            if (k < b.mb) {
+                const int64_t row = b.idx ? b.idx[k] : k;
+                if (net == 0) { pre_act = b.actions[row]; pre_logp = b.old_logp[row]; pre_adv = b.adv[row]; }
+                else pre_ret = b.ret[row];
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+
     {   // W2[j][i], rows as SB3 stores them, and its transpose; W1: 128-bit loads, all in flight
         float4 v2[4];
 #pragma unroll
@@ -196,14 +218,10 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
 
     const int64_t ntiles = (b.mb + kPpoTile - 1) / kPpoTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- gather the tile's observation rows (zero rows past the end of the minibatch)
-        if (t < 2 * kPpoTile) {
-            const int s = t >> 1, h = t & 1;
-            const int64_t k = tile * kPpoTile + s;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (k < b.mb) v = ((const float4 *)b.obs)[2 * (b.idx ? b.idx[k] : k) + h];
-            *(float4 *)(sX + s * 8 + 4 * h) = v;
-        }
+        // ---- this tile's gathered rows (zero rows past the end of the minibatch); next tile's gathers take off
+        if (t < 2 * kPpoTile) *(float4 *)(sX + (t >> 1) * 8 + 4 * (t & 1)) = pre_obs;
+        const float cur_act = pre_act, cur_logp = pre_logp, cur_adv = pre_adv, cur_ret = pre_ret;
+        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
         __syncthreads();
 
         // ---- layer 1: H1[s][j] = tanh(b1[j] + sum_c X[s][c] W1[j][c])
@@ -244,15 +262,14 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
                 const int64_t k = tile * kPpoTile + s;
                 float dy = 0.0f;
                 if (k < b.mb) {
-                    const int64_t row = b.idx ? b.idx[k] : k;
                     if (net == 0) {
                         // SB3 ppo.py train(): ratio = exp(log_prob - old_log_prob); policy_loss =
                         // -mean(min(adv * ratio, adv * clamp(ratio, 1 - clip, 1 + clip)))
-                        const float an = (b.adv[row] - adv_mean) * adv_scale;
-                        const float diff = b.actions[row] - y;
+                        const float an = (cur_adv - adv_mean) * adv_scale;
+                        const float diff = cur_act - y;
                         const float z2 = diff * diff * inv_var;
                         const float logp = -0.5f * z2 - log_std - 0.9189385332046727f;
-                        const float lr = logp - b.old_logp[row];
+                        const float lr = logp - cur_logp;
                         const float ratio = __expf(lr);
                         const float rc = fminf(fmaxf(ratio, 1.0f - clip_range), 1.0f + clip_range);
                         st_pg += -fminf(an * ratio, an * rc);
@@ -264,7 +281,7 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
                         st_dls += g * (z2 - 1.0f);                                  // d logp / d log_std
                     } else {
                         // value_loss = F.mse_loss(returns, values), weighted by vf_coef
-                        const float d = y - b.ret[row];
+                        const float d = y - cur_ret;
                         st_v += d * d;
                         dy = vf_coef * 2.0f * d * inv_mb;
                     }
