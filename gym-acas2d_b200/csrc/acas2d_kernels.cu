@@ -237,8 +237,11 @@ template <bool STOCHASTIC>
 __global__ void __launch_bounds__(kBlock, 2)
 policy_step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ weights,
                       const float *obs_in, float *__restrict__ actions_out, float *__restrict__ logp_out,
-                      const Sinks out, const float log_std, const uint64_t noise_seed, const uint64_t step_index)
+                      const Sinks out, const float log_std_value, const uint64_t noise_seed, const uint64_t step_offset,
+                      const PolicyDyn dyn)
 {
+    const float log_std = dyn.log_std ? *dyn.log_std : log_std_value;                 // live values for graph replays
+    const uint64_t step_index = step_offset + (dyn.step_base ? *dyn.step_base : 0);
     __shared__ __align__(16) float sw[kPolFloats];
     for (int q = threadIdx.x; q < kPolFloats; q += kBlock) sw[q] = weights[q];
     __syncthreads();
@@ -957,11 +960,44 @@ int acas2d_rollout_random(const acas2d_params *params, const acas2d_state *state
     return finish_launch();
 }
 
+namespace {
+// Function attributes (per device) of the policy kernels; cudaFuncGetAttributes also forces the lazily loaded
+// kernels in, so that a first launch may happen inside a CUDA-graph capture.
+int policy_prepare_device()
+{
+    static bool ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ready[dev & 63]) return 0;
+    cudaError_t err = cudaFuncSetAttribute(policy_step_n1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(policy_step_n1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    cudaFuncAttributes fa;
+    if ((err = cudaFuncGetAttributes(&fa, policy_step_n1_kernel<true>)) != cudaSuccess) return (int)err;
+    if ((err = cudaFuncGetAttributes(&fa, policy_step_n1_kernel<false>)) != cudaSuccess) return (int)err;
+    ready[dev & 63] = true;
+    return 0;
+}
+}  // namespace
+
 int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, const float *weights,
                        float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
                        float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
                        uint64_t noise_seed, uint64_t step_index, int32_t tensor_cores, void *stream)
 {
+    return acas2d_policy_step_dyn(params, state, weights, log_std, obs_in, actions_out, logp_out, obs_out, reward, done,
+                                  aux, stochastic, noise_seed, step_index, tensor_cores, nullptr, nullptr, stream);
+}
+
+int acas2d_policy_step_dyn(const acas2d_params *params, const acas2d_state *state, const float *weights,
+                           float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
+                           float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
+                           uint64_t noise_seed, uint64_t step_index, int32_t tensor_cores,
+                           const float *log_std_dev, const uint64_t *step_base_dev, void *stream)
+{
+    PolicyDyn dyn;
+    dyn.log_std = log_std_dev; dyn.step_base = step_base_dev;
     if (int e = check_args(params, state)) return e;
     if (params->n_traffic != 1 || state->min_sep) return ACAS2D_E_BAD_TRAFFIC;    // the trained actor takes 8 inputs
     if (state->num_envs == 0) return 0;
@@ -976,24 +1012,17 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (int e = policy_prepare_device()) return e;
     if (tensor_cores) {
-        static bool attr_set[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!attr_set[dev & 63]) {
-            cudaFuncSetAttribute(policy_step_n1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-            cudaFuncSetAttribute(policy_step_n1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-            attr_set[dev & 63] = true;
-        }
         long long g = (long long)sms * 4;                   // 4 CTAs/SM: 52 KB smem + 64 TMEM columns each
         const long long t = (S.B + kTcTile - 1) / kTcTile;
         if (g > t) g = t;
         if (stochastic)
             policy_step_n1_tc_kernel<true><<<(unsigned)g, kTcTile, kTcSmemBytes, st>>>(
-                P, S, weights, obs_in, actions_out, logp_out, out, log_std, noise_seed, step_index);
+                P, S, weights, obs_in, actions_out, logp_out, out, log_std, noise_seed, step_index, dyn);
         else
             policy_step_n1_tc_kernel<false><<<(unsigned)g, kTcTile, kTcSmemBytes, st>>>(
-                P, S, weights, obs_in, actions_out, logp_out, out, log_std, noise_seed, step_index);
+                P, S, weights, obs_in, actions_out, logp_out, out, log_std, noise_seed, step_index, dyn);
         return finish_launch();
     }
     long long grid = (long long)sms * 2;
@@ -1001,10 +1030,10 @@ int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, c
     if (grid > tiles) grid = tiles;
     if (stochastic)
         policy_step_n1_kernel<true><<<(unsigned)grid, kBlock, 0, st>>>(P, S, weights, obs_in, actions_out, logp_out, out,
-                                                                       log_std, noise_seed, step_index);
+                                                                       log_std, noise_seed, step_index, dyn);
     else
         policy_step_n1_kernel<false><<<(unsigned)grid, kBlock, 0, st>>>(P, S, weights, obs_in, actions_out, logp_out, out,
-                                                                        log_std, noise_seed, step_index);
+                                                                        log_std, noise_seed, step_index, dyn);
     return finish_launch();
 }
 
@@ -1093,7 +1122,11 @@ int launch_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const flo
 }
 }  // namespace
 
-int acas2d_ppo_prepare(void) { return ppo_prepare_device(); }
+int acas2d_ppo_prepare(void)
+{
+    if (int e = policy_prepare_device()) return e;
+    return ppo_prepare_device();
+}
 
 int acas2d_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const float *obs, const float *actions,
                     const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,

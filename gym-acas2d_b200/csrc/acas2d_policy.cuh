@@ -59,6 +59,12 @@ ACAS_HD float policy_mean(const float *w, const float *obs)
     return mean;
 }
 
+// Optional device-resident overrides of two by-value launch arguments, so that a captured rollout graph
+// (T policy-step launches) can be replayed while the learner keeps changing log_std and the noise counter
+// advances: log_std is read from *log_std (the learner's parameter block), the noise counter of the launch is
+// step_offset + *step_base.  Null pointers: the by-value arguments are used as they are.
+struct PolicyDyn { const float *log_std; const uint64_t *step_base; };
+
 // Standard normal from one Philox block (Box-Muller), keyed like the other streams:
 // key = noise_seed, counter = (global env id, step index, tag).
 ACAS_HD float policy_noise(uint64_t noise_seed, uint64_t gid, uint64_t step_index)

@@ -86,8 +86,11 @@ template <bool STOCHASTIC>
 __global__ void __launch_bounds__(kTcTile, 4)
 policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ weights,
                          const float *obs_in, float *__restrict__ actions_out, float *__restrict__ logp_out,
-                         const Sinks out, const float log_std, const uint64_t noise_seed, const uint64_t step_index)
+                         const Sinks out, const float log_std_value, const uint64_t noise_seed, const uint64_t step_offset,
+                         const PolicyDyn dyn)
 {
+    const float log_std = dyn.log_std ? *dyn.log_std : log_std_value;                 // live values for graph replays
+    const uint64_t step_index = step_offset + (dyn.step_base ? *dyn.step_base : 0);
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     float *sB1 = (float *)(smem + kTcB1), *sB2 = (float *)(smem + kTcB2), *sVec = (float *)(smem + kTcVec);

@@ -207,7 +207,8 @@ class BatchedACAS2D:
                     actions_out: Optional[torch.Tensor] = None, logp_out: Optional[torch.Tensor] = None,
                     obs_in: Optional[torch.Tensor] = None, full_outputs: bool = True, tensor_cores: bool = False,
                     obs_out: Optional[torch.Tensor] = None, reward_out: Optional[torch.Tensor] = None,
-                    done_out: Optional[torch.Tensor] = None):
+                    done_out: Optional[torch.Tensor] = None, log_std_ptr: Optional[int] = None,
+                    step_base_ptr: Optional[int] = None):
         """Closed-loop step: ``actor`` (``gym_ACAS2D.policy.MlpActor`` on this device) is evaluated on the
         current observation rows (default: this object's ``obs`` buffer, i.e. the previous step's output),
         its action -- ``model.predict(obs, deterministic=...)`` semantics, clipped to the Box -- is applied,
@@ -215,7 +216,9 @@ class BatchedACAS2D:
         log-probability go to ``actions_out`` / ``logp_out`` when given.  ``tensor_cores`` runs the two
         hidden layers as tcgen05 TF32 MMAs (TMEM accumulators) instead of float32 on the CUDA cores.
         ``obs_out`` / ``reward_out`` / ``done_out`` (uint8) redirect the step's outputs, e.g. into row t+1 /
-        row t of rollout buffers, so collecting a rollout copies nothing."""
+        row t of rollout buffers, so collecting a rollout copies nothing.  ``log_std_ptr`` / ``step_base_ptr``
+        (device pointers to a float32 / an int64) make the launch read log_std and the base of its noise
+        counter at run time -- what a captured rollout graph needs to stay valid while the policy is trained."""
         if actor.packed.device != self.device:
             actor.to(self.device)
         src = self.obs if obs_in is None else obs_in
@@ -224,23 +227,27 @@ class BatchedACAS2D:
         d_dst = self.done_u8 if done_out is None else done_out
         aux = self._aux_full if full_outputs else self._aux_lean
         with torch.cuda.device(self.device):
-            _native.check(self.lib.acas2d_policy_step(
-                self._p(), self._s(), actor.packed.data_ptr(), float(actor.log_std), src.data_ptr(),
+            _native.check(self.lib.acas2d_policy_step_dyn(
+                self._p(), self._s(), actor.packed.data_ptr(), 0.0 if log_std_ptr else float(actor.log_std), src.data_ptr(),
                 actions_out.data_ptr() if actions_out is not None else None,
                 logp_out.data_ptr() if logp_out is not None else None,
                 o_dst.data_ptr(), r_dst.data_ptr(), d_dst.data_ptr(), ctypes.byref(aux),
                 0 if deterministic else 1, int(noise_seed), int(step_index), 1 if tensor_cores else 0,
-                self._stream()), "acas2d_policy_step")
+                log_std_ptr, step_base_ptr, self._stream()), "acas2d_policy_step")
         self.launches += 1
         return o_dst, r_dst, d_dst.view(torch.bool)
 
     def collect_rollout(self, actor, n_steps: int, noise_seed: int = 0, step0: int = 0, tensor_cores: bool = True,
-                        buffers: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                        buffers: Optional[Dict[str, torch.Tensor]] = None, graph: bool = False) -> Dict[str, torch.Tensor]:
         """PPO-style rollout collection (what SB3's ``collect_rollouts`` does for the reference's
         ``PPO(...).learn``, training_main.py:44-52): ``n_steps`` stochastic closed-loop steps from the
         current observations, written straight into [T, B] buffers -- ``obs`` [T+1, B, L] (row t is what
         the actor saw at step t; row T bootstraps the value), ``actions``, ``logp``, ``rewards`` [T, B]
-        float32, ``dones`` [T, B] uint8.  One fused kernel per step, no copies, no host round trip."""
+        float32, ``dones`` [T, B] uint8.  One fused kernel per step, no copies, no host round trip.
+        ``graph``: the T launches are captured once into a CUDA graph (per actor block / buffers) and
+        replayed -- the rollout of a small batch is launch-bound otherwise; the launches read the actor's
+        weights, its log_std (``actor.log_std_ptr``) and the noise-counter base from device memory, so
+        the graph stays valid while the learner updates the policy in place."""
         T, B, L, dev = int(n_steps), self.num_envs, self.obs_dim, self.device
         if buffers is None:
             buffers = dict(obs=torch.empty(T + 1, B, L, dtype=torch.float32, device=dev),
@@ -248,14 +255,44 @@ class BatchedACAS2D:
                            logp=torch.empty(T, B, dtype=torch.float32, device=dev),
                            rewards=torch.empty(T, B, dtype=torch.float32, device=dev),
                            dones=torch.empty(T, B, dtype=torch.uint8, device=dev))
-        buffers["obs"][0].copy_(self.obs)
-        for t in range(T):
-            self.policy_step(actor, deterministic=False, noise_seed=noise_seed, step_index=step0 + t,
-                             actions_out=buffers["actions"][t], logp_out=buffers["logp"][t],
-                             obs_in=buffers["obs"][t], obs_out=buffers["obs"][t + 1],
-                             reward_out=buffers["rewards"][t], done_out=buffers["dones"][t],
-                             full_outputs=False, tensor_cores=tensor_cores)
-        self.obs.copy_(buffers["obs"][T])
+
+        def launch_all(step_index0: int, log_std_ptr, step_base_ptr):
+            buffers["obs"][0].copy_(self.obs)
+            for t in range(T):
+                self.policy_step(actor, deterministic=False, noise_seed=noise_seed, step_index=step_index0 + t,
+                                 actions_out=buffers["actions"][t], logp_out=buffers["logp"][t],
+                                 obs_in=buffers["obs"][t], obs_out=buffers["obs"][t + 1],
+                                 reward_out=buffers["rewards"][t], done_out=buffers["dones"][t],
+                                 full_outputs=False, tensor_cores=tensor_cores,
+                                 log_std_ptr=log_std_ptr, step_base_ptr=step_base_ptr)
+            self.obs.copy_(buffers["obs"][T])
+
+        if not graph:
+            launch_all(step0, getattr(actor, "log_std_ptr", None), None)
+            return buffers
+        key = (T, actor.packed.data_ptr(), int(noise_seed), bool(tensor_cores), buffers["obs"].data_ptr(),
+               buffers["actions"].data_ptr(), getattr(actor, "log_std_ptr", None))
+        if getattr(self, "_rollout_key", None) != key:
+            if actor.packed.device != dev:
+                actor.to(dev)
+            self._rollout_step_base = torch.zeros(1, dtype=torch.int64, device=dev)
+            with torch.cuda.device(dev):
+                _native.check(self.lib.acas2d_ppo_prepare(), "acas2d_ppo_prepare")    # attributes / module load before capture
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            g = torch.cuda.CUDAGraph()
+            launches_before = self.launches
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    launch_all(0, getattr(actor, "log_std_ptr", None), self._rollout_step_base.data_ptr())
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.launches = launches_before
+            self._rollout_graph, self._rollout_key = g, key
+            self._rollout_buffers = buffers                                           # keep the captured storages alive
+        self._rollout_step_base.fill_(int(step0))
+        self._rollout_graph.replay()
+        self.launches += T
         return buffers
 
     def capture_steps(self, actions: torch.Tensor, full_outputs: bool = False, num_steps: Optional[int] = None,

@@ -157,11 +157,16 @@ class ActorCritic(nn.Module):
 
 class BlockActor:
     """The actor half of a learner's live parameter block, in the shape ``BatchedACAS2D.policy_step`` expects
-    from an ``MlpActor`` (the block starts with the ``acas2d_policy_step`` weight layout, so nothing is copied)."""
+    from an ``MlpActor`` (the block starts with the ``acas2d_policy_step`` weight layout, so nothing is copied).
+    ``log_std_ptr`` lets the rollout kernels read the live log_std from the block itself."""
 
     def __init__(self, block: torch.Tensor):
         self.packed, self.device = block, block.device
-        self.log_std = float(block[_native.PPO_LOG_STD])          # one host read per rollout
+        self.log_std_ptr = block.data_ptr() + 4 * _native.PPO_LOG_STD
+
+    @property
+    def log_std(self) -> float:
+        return float(self.packed[_native.PPO_LOG_STD])           # a host read; the graphed rollout does not need it
 
     def to(self, device):
         if torch.device(device) != self.device:
@@ -501,7 +506,8 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
         actor = L.actor()
         env.clear_stats()
         t0 = time.perf_counter()
-        buffers = env.collect_rollout(actor, T, noise_seed=seed, step0=it * T, tensor_cores=tensor_cores, buffers=buffers)
+        buffers = env.collect_rollout(actor, T, noise_seed=seed, step0=it * T, tensor_cores=tensor_cores, buffers=buffers,
+                                      graph=cuda_graph and learner == "fused")
         torch.cuda.synchronize(dev)
         t_roll = time.perf_counter() - t0
         stats = env.episode_stats(reduce=True)

@@ -286,9 +286,20 @@ int acas2d_ppo_step(const acas2d_ppo_config *cfg, float *params, const float *ob
                     float *loss_stats, float *grad_out, int32_t rank, int32_t world, void *const *peer_exchange,
                     void *stream);
 
-/* Sets the kernels' function attributes and loads them on the current device (optional; makes the first
- * acas2d_ppo_* call legal inside a CUDA-graph capture). */
+/* Sets the function attributes of the PPO and policy-step kernels and loads them on the current device
+ * (optional; makes a first acas2d_ppo_* / acas2d_policy_step* call legal inside a CUDA-graph capture). */
 int acas2d_ppo_prepare(void);
+
+/* acas2d_policy_step with two launch arguments optionally read from device memory at run time, so that a
+ * CUDA graph of T captured policy steps (a whole PPO rollout) can be replayed while the learner changes the
+ * policy: log_std_dev (NULL: use log_std) points at the live log_std (e.g. params + 2 * ACAS2D_POLICY_FLOATS
+ * of the PPO parameter block; `weights` = the same block is re-read by every launch anyway), step_base_dev
+ * (NULL: 0) is added to step_index to form the noise counter of the launch. */
+int acas2d_policy_step_dyn(const acas2d_params *params, const acas2d_state *state, const float *weights,
+                           float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,
+                           float *reward, uint8_t *done, const acas2d_step_aux *aux, int32_t stochastic,
+                           uint64_t noise_seed, uint64_t step_index, int32_t tensor_cores,
+                           const float *log_std_dev, const uint64_t *step_base_dev, void *stream);
 
 /* Kernels launched by this library since load (all entry points). */
 int64_t acas2d_launch_count(void);

@@ -247,6 +247,39 @@ def test_epoch_graph_equals_eager_steps():
 
 
 @pytest.mark.gpu
+def test_graphed_rollout_equals_eager_rollout_while_the_policy_changes():
+    """``collect_rollout(graph=True)`` -- T captured policy-step launches replayed as one CUDA graph -- fills the
+    same buffers bit for bit as T eager launches, over two consecutive rollouts between which the learner's
+    parameter block (weights AND log_std, read from device memory by the captured launches) is modified."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import BatchedACAS2D
+    dev = torch.device("cuda", 0)
+    T, B = 40, 256 * 3 + 17
+    out = []
+    for graph in (False, True):
+        block = ppo.pack_params(init_state_dict()).to(dev)
+        actor = ppo.BlockActor(block)
+        env = BatchedACAS2D(B, device=dev, seed=21, auto_reset=True)
+        env.reset()
+        buf = None
+        snaps = []
+        for it in range(2):
+            buf = env.collect_rollout(actor, T, noise_seed=3, step0=it * T, tensor_cores=False, buffers=buf, graph=graph)
+            snaps.append({k: v.clone() for k, v in buf.items()})
+            block[:4801] *= 1.01                                     # the learner moves the policy in place ...
+            block[_native.PPO_LOG_STD] -= 0.25                       # ... and its log_std
+        out.append((snaps, env.ppos.clone(), env.episode_counters().clone()))
+    for a, b in zip(out[0][0], out[1][0]):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert not torch.equal(out[0][0][0]["actions"], out[0][0][1]["actions"])
+    std0 = float((out[0][0][0]["logp"]).mean()); std1 = float((out[0][0][1]["logp"]).mean())
+    assert std1 > std0 + 0.2                                         # smaller log_std -> larger log-densities: it was read live
+
+
+@pytest.mark.gpu
 def test_ppo_training_loop_fused_learner():
     """Short end-to-end run on the fused learner: finite statistics, the policy moves, episodes finish."""
     if not torch.cuda.is_available():
