@@ -526,7 +526,7 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
         t_learn = time.perf_counter() - t0
         rec = dict(iteration=it, env_steps=(it + 1) * n * world, episodes=stats["episodes"], mean_return=stats["mean_return"],
                    goal_rate=stats["goal_rate"], collision_rate=stats["collision_rate"], timeout_rate=stats["timeout_rate"],
-                   mean_length=stats["mean_length"], log_std=float(L.params[_native.PPO_LOG_STD]), rollout_s=t_roll,
+                   mean_length=stats["mean_length"], log_std=float(L.params.detach()[_native.PPO_LOG_STD]), rollout_s=t_roll,
                    learn_s=t_learn, rollout_env_steps_per_s=n * world / t_roll, **L.logged())
         history.append(rec)
         if log and rank == 0:
