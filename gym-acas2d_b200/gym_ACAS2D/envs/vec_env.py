@@ -39,6 +39,7 @@ class ACAS2DVecEnv(_VecEnvBase):
         else:
             self.num_envs, self.observation_space, self.action_space = int(num_envs), obs_space, act_space
         self._pending: Optional[np.ndarray] = None
+        self._fin = None                               # pinned staging of finished-episode data
         self.metadata = {"render.modes": []}
 
     # ------------------------------------------------------------------ SB3 numpy surface
@@ -56,15 +57,30 @@ class ACAS2DVecEnv(_VecEnvBase):
         infos: List[dict] = [{} for _ in range(self.num_envs)]
         idx = np.flatnonzero(done)
         if idx.size:
-            sel = torch.as_tensor(idx, device=self.core.device)
-            term = self.core.term_obs.index_select(0, sel).cpu().numpy()
-            ep_r = self.core.ep_return.index_select(0, sel).cpu().numpy()
-            ep_l = self.core.ep_length.index_select(0, sel).cpu().numpy()
-            oc = self.core.outcome.index_select(0, sel).cpu().numpy()
+            # finished episodes: the small per-env arrays whole, the terminal rows gathered, all four copies
+            # queued into pinned buffers behind one synchronisation
+            core, n = self.core, int(idx.size)
+            if self._fin is None:
+                B, L = self.num_envs, core.obs_dim
+                self._fin = dict(ret=torch.empty(B, dtype=torch.float32).pin_memory(),
+                                 length=torch.empty(B, dtype=torch.int32).pin_memory(),
+                                 outcome=torch.empty(B, dtype=torch.uint8).pin_memory(),
+                                 term=torch.empty(B, L, dtype=torch.float32).pin_memory(),
+                                 sel=torch.empty(B, dtype=torch.int64).pin_memory())
+            f = self._fin
+            f["sel"][:n] = torch.from_numpy(idx)
+            sel = f["sel"][:n].to(core.device, non_blocking=True)
+            f["term"][:n].copy_(core.term_obs.index_select(0, sel), non_blocking=True)
+            f["ret"].copy_(core.ep_return, non_blocking=True)
+            f["length"].copy_(core.ep_length, non_blocking=True)
+            f["outcome"].copy_(core.outcome, non_blocking=True)
+            torch.cuda.current_stream(core.device).synchronize()
+            term = f["term"][:n].numpy().copy()
+            ep_r, ep_l, oc = f["ret"].numpy(), f["length"].numpy(), f["outcome"].numpy()
             for k, i in enumerate(idx):
                 infos[i] = {"terminal_observation": term[k],
-                            "episode": {"r": float(ep_r[k]), "l": int(ep_l[k]) - 1},   # l = step() calls
-                            "outcome": int(oc[k])}
+                            "episode": {"r": float(ep_r[i]), "l": int(ep_l[i]) - 1},   # l = step() calls
+                            "outcome": int(oc[i])}
         return obs.copy(), reward.copy(), done.copy(), infos
 
     def step(self, actions: np.ndarray):
