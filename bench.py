@@ -334,71 +334,75 @@ def run_ours(args):
     # ---- secondary workloads (reported, not the headline)
     other = {}
     if N == 1 and not args.skip_other:
-        env.rollout_random(8, action_seed=1, step0=0)
-        fused_k, reps = 64, 4
-        ms_f = timed(lambda k: env.rollout_random(fused_k, action_seed=1, step0=100 + fused_k * k), reps)
-        other["fused_rollout_64_steps_per_launch"] = {"value": world * B * fused_k * reps / (ms_f * 1e-3), "unit": UNIT,
-                                                      "note": "in-kernel Philox actions, state in registers, no per-step outputs"}
-        # closed-loop rollout: the reference's trained actor (8-64-64-1 tanh MLP) fused with the env step
-        from gym_ACAS2D.policy import MlpActor
-        fixture = os.path.join(ROOT, "tests", "golden", "ppo_policy_1048576_11.npz")
-        actor = MlpActor.from_file(fixture, dev) if os.path.exists(fixture) else MlpActor.random(0, dev)
-        pol_steps = 16
-        for k in range(3):
-            env.policy_step(actor, deterministic=False, noise_seed=5, step_index=k, full_outputs=False)
-        ms_p = timed(lambda k: env.policy_step(actor, deterministic=False, noise_seed=5, step_index=10 + k,
-                                               full_outputs=False), pol_steps)
-        other["policy_rollout_fused_mlp_env_step"] = {
-            "value": world * B * pol_steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / pol_steps,
-            "note": "BASELINE config 5 inner loop: SB3 MlpPolicy actor (fp32, CUDA cores) + Gaussian noise + clip + env "
-                    "step in one kernel per step; no host round trip"}
-        for k in range(3):
-            env.policy_step(actor, deterministic=False, noise_seed=5, step_index=k, full_outputs=False, tensor_cores=True)
-        ms_t = timed(lambda k: env.policy_step(actor, deterministic=False, noise_seed=5, step_index=40 + k,
-                                               full_outputs=False, tensor_cores=True), 4 * pol_steps)
-        other["policy_rollout_tcgen05_mlp_env_step"] = {
-            "value": world * B * 4 * pol_steps / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / (4 * pol_steps),
-            "note": "same, hidden layers as tcgen05.mma kind::tf32 with TMEM accumulators (128 envs per CTA tile)"}
-        # the SB3-style numpy VecEnv surface (host arrays in / out, per-env info dicts) at 4096 envs
-        from gym_ACAS2D.envs import ACAS2DVecEnv
-        import numpy as np
-        venv = ACAS2DVecEnv(4096, device=dev, seed=13)
-        venv.reset()
-        ex = venv.core.extract_state()                 # stagger the episodes: finished envs (info dicts, terminal rows) every step
-        ex["steps"][:] = 1 + (np.arange(4096) * 7) % 900
-        venv.core.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
-        va = np.zeros((4096, 1), np.float32)
-        for _ in range(5):
-            venv.step(va)
-        t0 = time.perf_counter()
-        for _ in range(200):
-            venv.step(va)
-        dt = time.perf_counter() - t0
-        other["vecenv_numpy_surface_4096_envs"] = {"value": world * 4096 * 200 / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / 200,
-                                                   "note": "ACAS2DVecEnv.step(np actions) -> np obs / rewards / dones + list of info dicts, ~7 episodes ending per step; wall clock"}
-        small = BatchedACAS2D(4096, n_traffic=1, device=dev, seed=13, env_id_offset=0, auto_reset=True)
-        small.reset()
-        sgraph = small.capture_steps(actions[:, :4096].contiguous(), num_steps=200)      # 200 steps per replay
-        sgraph.replay()
-        ms_s = timed(lambda k: sgraph.replay(), 10)
-        other["config2_4096_envs_cuda_graph"] = {"value": world * 4096 * 200 * 10 / (ms_s * 1e-3), "unit": UNIT,
-                                                 "note": "BASELINE config 2 batch: launch-bound, 200-step CUDA graph replay"}
+        try:                                           # the secondary lines must never cost the run its headline line
+            env.rollout_random(8, action_seed=1, step0=0)
+            fused_k, reps = 64, 4
+            ms_f = timed(lambda k: env.rollout_random(fused_k, action_seed=1, step0=100 + fused_k * k), reps)
+            other["fused_rollout_64_steps_per_launch"] = {"value": world * B * fused_k * reps / (ms_f * 1e-3), "unit": UNIT,
+                                                          "note": "in-kernel Philox actions, state in registers, no per-step outputs"}
+            # closed-loop rollout: the reference's trained actor (8-64-64-1 tanh MLP) fused with the env step
+            from gym_ACAS2D.policy import MlpActor
+            fixture = os.path.join(ROOT, "tests", "golden", "ppo_policy_1048576_11.npz")
+            actor = MlpActor.from_file(fixture, dev) if os.path.exists(fixture) else MlpActor.random(0, dev)
+            pol_steps = 16
+            for k in range(3):
+                env.policy_step(actor, deterministic=False, noise_seed=5, step_index=k, full_outputs=False)
+            ms_p = timed(lambda k: env.policy_step(actor, deterministic=False, noise_seed=5, step_index=10 + k,
+                                                   full_outputs=False), pol_steps)
+            other["policy_rollout_fused_mlp_env_step"] = {
+                "value": world * B * pol_steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / pol_steps,
+                "note": "BASELINE config 5 inner loop: SB3 MlpPolicy actor (fp32, CUDA cores) + Gaussian noise + clip + env "
+                        "step in one kernel per step; no host round trip"}
+            for k in range(3):
+                env.policy_step(actor, deterministic=False, noise_seed=5, step_index=k, full_outputs=False, tensor_cores=True)
+            ms_t = timed(lambda k: env.policy_step(actor, deterministic=False, noise_seed=5, step_index=40 + k,
+                                                   full_outputs=False, tensor_cores=True), 4 * pol_steps)
+            other["policy_rollout_tcgen05_mlp_env_step"] = {
+                "value": world * B * 4 * pol_steps / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / (4 * pol_steps),
+                "note": "same, hidden layers as tcgen05.mma kind::tf32 with TMEM accumulators (128 envs per CTA tile)"}
+            # the SB3-style numpy VecEnv surface (host arrays in / out, per-env info dicts) at 4096 envs
+            from gym_ACAS2D.envs import ACAS2DVecEnv
+            import numpy as np
+            venv = ACAS2DVecEnv(4096, device=dev, seed=13)
+            venv.reset()
+            ex = venv.core.extract_state()                 # stagger the episodes: finished envs (info dicts, terminal rows) every step
+            ex["steps"][:] = 1 + (np.arange(4096) * 7) % 900
+            venv.core.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+            va = np.zeros((4096, 1), np.float32)
+            for _ in range(5):
+                venv.step(va)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                venv.step(va)
+            dt = time.perf_counter() - t0
+            other["vecenv_numpy_surface_4096_envs"] = {"value": world * 4096 * 200 / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / 200,
+                                                       "note": "ACAS2DVecEnv.step(np actions) -> np obs / rewards / dones + list of info dicts, ~7 episodes ending per step; wall clock"}
+            small = BatchedACAS2D(4096, n_traffic=1, device=dev, seed=13, env_id_offset=0, auto_reset=True)
+            small.reset()
+            sgraph = small.capture_steps(actions[:, :4096].contiguous(), num_steps=200)      # 200 steps per replay
+            sgraph.replay()
+            ms_s = timed(lambda k: sgraph.replay(), 10)
+            other["config2_4096_envs_cuda_graph"] = {"value": world * 4096 * 200 * 10 / (ms_s * 1e-3), "unit": UNIT,
+                                                     "note": "BASELINE config 2 batch: launch-bound, 200-step CUDA graph replay"}
 
-        if world == 1:
-            # PPO learner (BASELINE config 5): one epoch of 32 minibatch gradient steps, this repo's
-            # kernels vs the same arithmetic in torch autograd (both replayed from CUDA graphs)
-            from gym_ACAS2D import ppo as _ppo
-            n_l, mbs = 131072, 32
-            data = [torch.rand(n_l, 8, device=dev) * 2 - 1, torch.randn(n_l, device=dev), -torch.rand(n_l, device=dev) - 0.5,
-                    torch.randn(n_l, device=dev), torch.randn(n_l, device=dev)]
-            for name, cls in (("fused_kernels", _ppo.FusedLearner), ("torch_autograd_cuda_graph", _ppo.TorchLearner)):
-                learner = cls(dev, None, None, cuda_graph=True)
-                learner.bind(*data, mbs)
-                learner.epoch()
-                ms_l = timed(lambda k: learner.epoch(), 3)
-                other["ppo_learner_" + name] = {
-                    "us_per_gradient_step": 1e3 * ms_l / (3 * mbs), "minibatch": n_l // mbs,
-                    "note": "advantage normalisation + forward/backward of actor and critic + grad-norm clip + Adam"}
+            if world == 1:
+                # PPO learner (BASELINE config 5): one epoch of 32 minibatch gradient steps, this repo's
+                # kernels vs the same arithmetic in torch autograd (both replayed from CUDA graphs)
+                from gym_ACAS2D import ppo as _ppo
+                n_l, mbs = 131072, 32
+                data = [torch.rand(n_l, 8, device=dev) * 2 - 1, torch.randn(n_l, device=dev), -torch.rand(n_l, device=dev) - 0.5,
+                        torch.randn(n_l, device=dev), torch.randn(n_l, device=dev)]
+                for name, cls in (("fused_kernels", _ppo.FusedLearner), ("torch_autograd_cuda_graph", _ppo.TorchLearner)):
+                    learner = cls(dev, None, None, cuda_graph=True)
+                    learner.bind(*data, mbs)
+                    learner.epoch()
+                    ms_l = timed(lambda k: learner.epoch(), 3)
+                    other["ppo_learner_" + name] = {
+                        "us_per_gradient_step": 1e3 * ms_l / (3 * mbs), "minibatch": n_l // mbs,
+                        "note": "advantage normalisation + forward/backward of actor and critic + grad-norm clip + Adam"}
+        except Exception as exc:                       # noqa: BLE001
+            other["error"] = repr(exc)
+            torch.cuda.synchronize()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
