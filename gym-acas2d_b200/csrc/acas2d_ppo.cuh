@@ -10,7 +10,7 @@
 //
 // One gradient step = two kernels:
 //   ppo_grad_kernel       forward + backward of BOTH networks over the minibatch: grid (G, 2), blockIdx.y
-//                         picks actor or critic (their losses do not interact), each CTA walks 64-sample
+//                         picks actor or critic (their losses do not interact), each CTA walks 32-sample
 //                         tiles, everything in shared memory, weight gradients accumulated in registers
 //                         across its tiles, one partial-gradient row per CTA; the actor CTAs first take the
 //                         mean / unbiased std of the minibatch's advantages (two passes, every CTA the same)
@@ -22,7 +22,7 @@
 // plus, for callers that exchange gradients themselves (torch.distributed all-reduce), the same work split
 // as ppo_grad_kernel -> ppo_reduce_kernel (-> all-reduce) -> ppo_adam_kernel.
 // The matrices are 64-wide: a minibatch step is ~0.1 GFLOP, launch/latency-bound, so this is float32 on
-// the CUDA cores (bit-comparable with the torch float32 reference) rather than TF32 tensor-core code.
+// the CUDA cores (within 2e-4 of the torch float32 reference's gradients) rather than TF32 tensor-core code.
 // Everything is deterministic: no floating-point atomics.
 #pragma once
 
@@ -36,8 +36,9 @@ constexpr int kPpoParams = ACAS2D_PPO_PARAM_FLOATS;
 constexpr int kPpoPartial = ACAS2D_PPO_PARTIAL_FLOATS;
 constexpr int kPpoMaxCtas = ACAS2D_PPO_MAX_CTAS;
 constexpr int kPpoTile = 32, kPpoThreads = 256;     // gradient kernel: 32-sample tiles -> two CTAs per SM (16 warps) at
-                                                    // a 4096-row minibatch; with 64-sample tiles one CTA per SM ran at
-                                                    // 12 % occupancy, every phase latency-bound (ncu: profiles/)
+                                                    // a 4096-row minibatch.  Measured equal to 64-sample tiles (one
+                                                    // CTA per SM, 12 % occupancy): the serial chain of phases bounds
+                                                    // the kernel, not occupancy; kept for small minibatches
 constexpr int kPpoTq = kPpoTile / 16;               // sample rows per thread in the 16 x 16 thread grid
 constexpr int kPpoLps = kPpoThreads / kPpoTile;     // lanes per sample in the output-unit phase
 constexpr int kPpoValTile = 64;                     // critic-forward kernel: 64-row tiles
