@@ -70,8 +70,9 @@ def _stub_modules():
     return {"gym": gym, "gym.spaces": spaces, "gym.envs": envs, "gym.envs.registration": registration, "pygame": pg}
 
 
-def load(n_traffic: int = 1):
-    """Import the reference with MIN/MAX_TRAFFIC = n_traffic; returns the ``gym_ACAS2D`` module.
+def load(n_traffic: int = 1, **settings_overrides):
+    """Import the reference with MIN/MAX_TRAFFIC = n_traffic (and any other settings.py constant
+    overridden the same way, e.g. AIRSPEED_FACTOR_MIN / MAX); returns the ``gym_ACAS2D`` module.
 
     The reference star-imports its settings at import time, so a different traffic
     count needs a fresh import (Config)."""
@@ -85,6 +86,10 @@ def load(n_traffic: int = 1):
     try:
         settings = importlib.import_module("gym_ACAS2D.settings")
         settings.MIN_TRAFFIC = settings.MAX_TRAFFIC = int(n_traffic)
+        for key, value in settings_overrides.items():
+            if not hasattr(settings, key):
+                raise KeyError(key)
+            setattr(settings, key, value)
         pkg = importlib.import_module("gym_ACAS2D")
         importlib.import_module("gym_ACAS2D.envs")
     finally:

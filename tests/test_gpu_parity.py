@@ -571,3 +571,34 @@ def test_tiled_kernel_sharding_invariance_at_scale(cuda):
     assert torch.equal(full.episode_counters(), lo.episode_counters() + hi.episode_counters())
     assert torch.equal(full.min_sep[B // 2:], hi.min_sep) and torch.equal(full.thot[: B // 2], lo.thot)
     assert full.episode_counters()[0].item() > 10000
+
+
+@pytest.mark.parametrize("n", [1, 8])
+def test_unequal_speeds_q3_on_the_gpu(cuda, n):
+    """Q3 (kinematics.py:74) through the CUDA kernels: intruders at 0.6 .. 1.4 x the player's airspeed, spawned
+    and injected (float64 residual path) states, auto-reset; flags bit-exact, floats within the tolerances.
+    The oracle is pinned to the unmodified reference for this setting in tests/test_oracle_golden.py."""
+    over = dict(AIRSPEED_FACTOR_MIN=0.6, AIRSPEED_FACTOR_MAX=1.4)
+    B, seed, off = 256 * 3 + 5, 29, 500
+    env = make(B, n, seed=seed, env_id_offset=off, auto_reset=True, **over)
+    orc = Oracle(n, **over)
+    st = orc.new_state(B)
+    orc.spawn_philox(st, seed, off)
+    assert np.abs(npy(env.reset()) - orc.observe(st)).max() < parity.TOL_OBS_CPA
+    rng = np.random.default_rng(3)
+    ex = env.extract_state()
+    assert np.abs(ex["traffic"][:, :, 2] - 200.0).max() > 50.0
+    ex["traffic"][::2, :, 2] = rng.uniform(90.0, 310.0, ex["traffic"][::2, :, 2].shape)
+    env.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    st["traffic"][::2, :, 2] = ex["traffic"][::2, :, 2]
+    rep = parity.ParityReport()
+    for t in range(400):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        obs, rew, done = env.step(torch.from_numpy(a).cuda())
+        o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, a.astype(np.float64), seed, off)
+        d = f & FLAG_DONE > 0
+        assert np.array_equal(npy(done), d)
+        parity.compare_step(rep, np.where(d[:, None], npy(env.term_obs), npy(obs)), npy(rew), npy(env.flags),
+                            np.where(d[:, None], term, o), r, f)
+    parity.assert_flags_exact(rep)
+    assert rep.steps == 400 * B

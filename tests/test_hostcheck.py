@@ -236,3 +236,34 @@ def test_observe_is_the_reset_observation_of_an_injected_state():
     assert np.abs(got[:, :5] - ref[:, :5]).max() < parity.TOL_OBS_BASE
     assert np.nanmax(np.abs(got[:, 5:] - ref[:, 5:])) < parity.TOL_OBS_CPA
     assert np.array_equal(hb.extract_state()["steps"], steps)       # state untouched
+
+
+@pytest.mark.parametrize("n,variant", [(1, 0), (3, 1)])
+def test_unequal_speeds_q3(n, variant):
+    """Q3 in the product's per-env source: intruders at 0.6 .. 1.4 x the player's airspeed (the oracle is pinned
+    to the unmodified reference for this case by test_oracle_matches_live_reference_with_unequal_speeds).
+    Spawned and injected states, auto-reset, flags bit-exact, observations / rewards within the tolerances."""
+    over = dict(AIRSPEED_FACTOR_MIN=0.6, AIRSPEED_FACTOR_MAX=1.4)
+    B, seed, off = 64, 29, 500
+    hb = HostBatch(B, n, seed=seed, env_id_offset=off, auto_reset=True, variant=variant, **over)
+    orc = Oracle(n, **over)
+    st = orc.new_state(B)
+    orc.spawn_philox(st, seed, off)
+    assert np.abs(hb.reset() - orc.observe(st)).max() < parity.TOL_OBS_CPA
+    assert np.abs(st["traffic"][:, :, 2] - 200.0).max() > 50.0
+    # half of the envs continue from injected float64 states with arbitrary intruder speeds (residual path)
+    rng = np.random.default_rng(3)
+    ex = hb.extract_state()
+    ex["traffic"][::2, :, 2] = rng.uniform(90.0, 310.0, ex["traffic"][::2, :, 2].shape)
+    hb.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    st["traffic"][::2, :, 2] = ex["traffic"][::2, :, 2]
+    rep = parity.ParityReport()
+    for t in range(500):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        obs, rew, done = hb.step(a)
+        o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, a.astype(np.float64), seed, off)
+        d = f & FLAG_DONE > 0
+        assert np.array_equal(done, d)
+        parity.compare_step(rep, np.where(d[:, None], hb.term_obs, obs), rew, hb.flags, np.where(d[:, None], term, o), r, f)
+    parity.assert_flags_exact(rep)
+    assert rep.steps == 500 * B

@@ -169,3 +169,42 @@ def test_oracle_matches_live_reference(n):
         assert consts == {k: DEFAULTS[k] if k not in ("MIN_TRAFFIC", "MAX_TRAFFIC") else n for k in DEFAULTS}
     finally:
         ref_shim.unload()
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+def test_oracle_matches_live_reference_with_unequal_speeds():
+    """Q3 (kinematics.py:74): the closing-speed look-ahead multiplies the INTRUDER's sine by the PLAYER's
+    airspeed.  Invisible at the default speed factors (1..1); here the unmodified reference runs with
+    AIRSPEED_FACTOR_MIN / MAX = 0.6 / 1.4 so that intruders fly at other speeds than the player."""
+    over = dict(AIRSPEED_FACTOR_MIN=0.6, AIRSPEED_FACTOR_MAX=1.4)
+    ref_shim.load(2, **over)
+    try:
+        from gym_ACAS2D.envs.environment import ACAS2DEnv
+        orc = Oracle(2, **over)
+        random.seed(7)
+        arng = np.random.default_rng(7)
+        speeds = []
+        with ref_shim.quiet():
+            env = ACAS2DEnv()
+            for ep in range(4):
+                obs = env.reset()
+                g = env.game
+                st = orc.new_state(1)
+                st["player"][0] = (g.player.x, g.player.y, g.player.v_air, g.player.psi, 0.0)
+                for i in range(2):
+                    t = g.traffic[i]
+                    st["traffic"][0, i] = (t.x, t.y, t.v_air, t.psi)
+                    speeds.append(t.v_air)
+                assert np.abs(orc.observe(st)[0] - obs).max() < 1e-14
+                for k in range(1100):
+                    a = float(np.float32(arng.uniform(-1, 1)))
+                    ro, rr, rd, _ = env.step(np.array([a]))
+                    co, cr, cf, coc = orc.step(st, np.array([a]))
+                    assert bool(cf[0] & FLAG_DONE) == rd
+                    assert np.nanmax(np.abs(ro - co[0])) < 1e-13 and abs(rr - cr[0]) < 1e-12
+                    if rd:
+                        assert g.outcome == coc[0] and g.steps == st["steps"][0]
+                        break
+        assert max(abs(v - 200.0) for v in speeds) > 20.0           # the intruders really flew at other speeds
+    finally:
+        ref_shim.unload()
