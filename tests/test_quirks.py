@@ -1,0 +1,180 @@
+"""Directed corner cases for the reference's bug-compat list:
+one ``step()`` from an injected state, compared across
+  * the unmodified reference (imported under the gym / pygame stand-ins; build container only),
+  * the float64 oracle,
+  * the product's per-env source compiled with g++ (``tests/hostcheck``),
+  * the CUDA kernels through the C ABI (``-m gpu``).
+The geometry of every case is made of small integers so that the strict thresholds (Q8) sit exactly on a
+representable value in all four implementations."""
+import numpy as np
+import pytest
+
+from oracle import ref_shim
+from oracle.acas2d_oracle import FLAG_DONE, Oracle
+from tests import parity
+from tests.hostcheck import HostBatch
+
+FLAG_COLLISION, FLAG_GOAL, FLAG_TIMEOUT, FLAG_OOB = 1, 2, 4, 16
+GOAL = (1456.0, 500.0)                      # WIDTH - GOAL_RADIUS, HEIGHT / 2 (game.py:80-81)
+
+# name -> dict(player=(x, y, psi), traffic=[(x, y, v, psi), ...], steps, action, expect=(flags & 15, outcome))
+CASES = {
+    # Q9: both bonuses on the same step (-1000 + 1000); outcome priority collision > goal
+    "q9_collision_and_goal": dict(player=(1400.0, 500.0, 0.0), traffic=[(1452.0, 500.0, 200.0, 180.0)], steps=300,
+                                  action=0.0, expect=(FLAG_COLLISION | FLAG_GOAL | 8, 2)),
+    # Q5 / Q6 / Q9: the 1000th step() call times out (steps == 1001, discount -0.001); the collision bonus is
+    # still added; outcome priority timeout > collision
+    "q9_timeout_with_collision": dict(player=(700.0, 500.0, 0.0), traffic=[(752.0, 500.0, 200.0, 180.0)], steps=1000,
+                                      action=0.0, expect=(FLAG_COLLISION | FLAG_TIMEOUT | 8, 3)),
+    # Q8: strict thresholds -- separation exactly 96 is NOT a collision ...
+    "q8_separation_exactly_96": dict(player=(500.0, 500.0, 0.0), traffic=[(600.0, 500.0, 200.0, 180.0)], steps=10,
+                                     action=0.0, expect=(0, 0)),
+    # ... one part in 1e11 closer is
+    "q8_separation_just_below_96": dict(player=(500.0, 500.0, 0.0), traffic=[(600.0 - 1e-9, 500.0, 200.0, 180.0)], steps=10,
+                                        action=0.0, expect=(FLAG_COLLISION | 8, 2)),
+    # goal distance exactly 144 is NOT the goal
+    "q8_goal_distance_exactly_144": dict(player=(1310.0, 500.0, 0.0), traffic=[(100.0, 100.0, 200.0, 90.0)], steps=10,
+                                         action=0.0, expect=(0, 0)),
+    "q8_goal_distance_just_below_144": dict(player=(1310.0 + 1e-9, 500.0, 0.0), traffic=[(100.0, 100.0, 200.0, 90.0)], steps=10,
+                                            action=0.0, expect=(FLAG_GOAL | 8, 1)),
+    # Q12: equal velocities -> arctan(0/0) -> d_cpa is NaN in the observation, min(1, nan) == 1 in the reward
+    "q12_equal_velocities": dict(player=(400.0, 500.0, 10.0), traffic=[(700.0, 300.0, 200.0, 10.0)], steps=50,
+                                 action=0.0, expect=(0, 0)),
+    # Q12: arctan, not arctan2 -- relative velocity pointing in -x flips the sign convention of d_cpa
+    "q12_negative_v12x": dict(player=(800.0, 500.0, 180.0), traffic=[(400.0, 380.0, 200.0, 20.0)], steps=50,
+                              action=0.25, expect=(0, 0)),
+    # Q13: leaving the map never ends an episode (informational flag only)
+    "q13_out_of_map": dict(player=(1.0, 500.0, 180.0), traffic=[(900.0, 100.0, 200.0, 90.0)], steps=50,
+                           action=0.0, expect=(0, 0)),
+    # Q19 / Q2: actions are not clipped; the closing-speed look-ahead turns by a different amount than the aircraft
+    "q19_unclipped_action": dict(player=(300.0, 400.0, 5.0), traffic=[(900.0, 700.0, 200.0, 200.0)], steps=50,
+                                 action=3.7, expect=(0, 0)),
+    "q2_full_deflection_converging": dict(player=(300.0, 500.0, 350.0), traffic=[(700.0, 450.0, 200.0, 175.0)], steps=50,
+                                          action=-1.0, expect=(0, 0)),
+    # Q7: only traffic[0] shapes the reward (two orders of the same two intruders), all intruders collide
+    "q7_near_intruder_first": dict(player=(300.0, 500.0, 0.0), traffic=[(600.0, 520.0, 200.0, 185.0), (1500.0, 100.0, 200.0, 90.0)],
+                                   steps=50, action=0.1, expect=(0, 0)),
+    "q7_near_intruder_second": dict(player=(300.0, 500.0, 0.0), traffic=[(1500.0, 100.0, 200.0, 90.0), (600.0, 520.0, 200.0, 185.0)],
+                                    steps=50, action=0.1, expect=(0, 0)),
+    "q7_collision_with_second": dict(player=(300.0, 500.0, 0.0), traffic=[(1500.0, 100.0, 200.0, 90.0), (380.0, 500.0, 200.0, 180.0)],
+                                     steps=50, action=0.0, expect=(FLAG_COLLISION | 8, 2)),
+}
+
+
+def run_oracle(case):
+    n = len(case["traffic"])
+    orc = Oracle(n)
+    st = orc.new_state(1)
+    x, y, psi = case["player"]
+    st["player"][0] = (x, y, 200.0, psi, 0.0)
+    st["traffic"][0] = case["traffic"]
+    st["steps"][0] = case["steps"]
+    with np.errstate(all="ignore"):
+        obs, rew, flags, outcome = orc.step(st, np.array([case["action"]]))
+    return obs[0], float(rew[0]), int(flags[0]), int(outcome[0])
+
+
+def run_host(case, cls=HostBatch, **kw):
+    n = len(case["traffic"])
+    hb = cls(1, n, auto_reset=False, **kw)
+    hb.inject_state(np.array([case["player"]]), np.array([case["traffic"]]), np.array([case["steps"]], np.int32), np.zeros(1))
+    obs, rew, done = hb.step(np.array([case["action"]], np.float32))
+    to = (lambda a: a.detach().cpu().numpy()) if not isinstance(obs, np.ndarray) else (lambda a: np.asarray(a))
+    flags = int(to(hb.flags)[0])
+    return to(obs)[0].astype(np.float64), float(to(rew)[0]), flags, int(to(hb.outcome)[0]) if flags & 8 else 0
+
+
+def run_reference(case):
+    """The unmodified reference: poke the game's attributes (what its own scripts do), one env.step."""
+    n = len(case["traffic"])
+    ref_shim.load(n)
+    try:
+        from gym_ACAS2D.envs.environment import ACAS2DEnv
+        with ref_shim.quiet(), np.errstate(all="ignore"):
+            env = ACAS2DEnv()
+            env.reset()
+            g = env.game
+            g.player.x, g.player.y, g.player.psi = case["player"]
+            g.player.a_lat = 0.0
+            for t, (x, y, v, psi) in zip(g.traffic, case["traffic"]):
+                t.x, t.y, t.v_air, t.psi = x, y, v, psi
+            g.steps = case["steps"]
+            g.total_reward = 0.0
+            obs, rew, done, _ = env.step(np.array([case["action"]]))
+        return np.asarray(obs, np.float64), float(rew), bool(done), int(g.outcome) if done else 0
+    finally:
+        ref_shim.unload()
+
+
+def check_against_oracle(name, got, want):
+    obs, rew, flags, outcome = got
+    wobs, wrew, wflags, woutcome = want
+    assert flags & 15 == wflags & 15 and outcome == woutcome, name
+    assert np.array_equal(np.isnan(obs), np.isnan(wobs)), name
+    with np.errstate(invalid="ignore"):
+        err = np.abs(obs - wobs)
+    assert np.nanmax(err[:6]) < parity.TOL_OBS_BASE and np.nanmax(err) < parity.TOL_OBS_CPA, (name, err)
+    assert abs(rew - wrew) < parity.TOL_REWARD_ABS + parity.TOL_REWARD_REL * abs(wrew) + 1e-4 * (abs(wrew) >= 900), (name, rew, wrew)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_does_what_the_case_says(name):
+    case = CASES[name]
+    obs, rew, flags, outcome = run_oracle(case)
+    assert (flags & 15, outcome) == case["expect"], (name, flags, outcome)
+    if name == "q9_collision_and_goal":
+        assert abs(rew) < 2.0                                  # shaped reward -1000 + 1000
+    if name == "q9_timeout_with_collision":
+        assert -1000.0 - 1e-2 < rew < -1000.0 + 1e-2 and abs(obs[0] - 1.001) < 1e-15     # Q5 / Q6
+    if name == "q12_equal_velocities":
+        assert np.isnan(obs[6]) and obs[7] == 0.0 and np.isfinite(rew) and rew > 0.0
+    if name == "q13_out_of_map":
+        assert not flags & FLAG_DONE
+    if name == "q7_near_intruder_second":
+        other = run_oracle(CASES["q7_near_intruder_first"])
+        assert abs(other[1] - rew) > 1e-3 and other[2] == flags    # the reward depends on which intruder is traffic[0]
+        assert np.allclose(other[0][5:8], obs[8:11]) and np.allclose(other[0][8:11], obs[5:8])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_equals_the_unmodified_reference(name):
+    case = CASES[name]
+    robs, rrew, rdone, routcome = run_reference(case)
+    obs, rew, flags, outcome = run_oracle(case)
+    assert rdone == bool(flags & FLAG_DONE) and routcome == outcome, name
+    assert np.array_equal(np.isnan(robs), np.isnan(obs))
+    with np.errstate(invalid="ignore"):
+        assert np.nanmax(np.abs(robs - obs)) < 1e-13, (name, robs, obs)
+    assert abs(rrew - rew) < 1e-12 * max(1.0, abs(rrew)), (name, rrew, rew)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_product_source_on_the_cpu(name):
+    case = CASES[name]
+    n = len(case["traffic"])
+    for variant in ((0, 1) if n == 1 else (1,)):
+        check_against_oracle(name, run_host(case, variant=variant), run_oracle(case))
+    if name == "q13_out_of_map":
+        assert run_host(case)[2] & FLAG_OOB
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_kernels(name):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import BatchedACAS2D
+
+    class Gpu(BatchedACAS2D):
+        def __init__(self, B, n, auto_reset=False):
+            super().__init__(B, n_traffic=n, device="cuda:0", auto_reset=auto_reset)
+
+        def step(self, a):
+            return super().step(torch.from_numpy(np.asarray(a, np.float32)).cuda())
+
+    case = CASES[name]
+    check_against_oracle(name, run_host(case, cls=Gpu), run_oracle(case))
+    if name == "q13_out_of_map":
+        assert run_host(case, cls=Gpu)[2] & FLAG_OOB
