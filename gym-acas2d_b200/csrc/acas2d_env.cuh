@@ -270,8 +270,9 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
     const bool coll = en.d2 < P.coll_d2;                                   // game.py:187 (strict, Q8)
     const bool goal = v.dg2 < P.goal_r2;                                   // game.py:192
     const bool tout = steps > P.max_steps;                                 // game.py:183
-    if (coll) r += P.reward_collision;                                     // game.py:279-284 (Q9)
-    if (goal) r += P.reward_goal;
+    // game.py:279-284 (Q9): both bonuses can fall on one step; summed first so that -1000 + 1000 does not
+    // round the shaped reward to the float32 spacing at 1000
+    r += (coll ? P.reward_collision : 0.0f) + (goal ? P.reward_goal : 0.0f);
     const float ret = e.ret + r;                                           // game.py:287
     const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
                         : goal ? ACAS2D_OUTCOME_GOAL : 0;                  // game.py:297-310
@@ -399,8 +400,9 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
     float r = shaped_reward(P, p, v, e0, steps);
     const bool goal = v.dg2 < P.goal_r2;
     const bool tout = steps > P.max_steps;
-    if (coll) r += P.reward_collision;
-    if (goal) r += P.reward_goal;
+    // game.py:279-284 (Q9): both bonuses can fall on one step; summed first so that -1000 + 1000 does not
+    // round the shaped reward to the float32 spacing at 1000
+    r += (coll ? P.reward_collision : 0.0f) + (goal ? P.reward_goal : 0.0f);
     float ret = pa.ep_return + r;
     const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
                         : goal ? ACAS2D_OUTCOME_GOAL : 0;

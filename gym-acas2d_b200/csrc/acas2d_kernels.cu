@@ -449,8 +449,9 @@ ACAS_UNROLL(ACAS2D_TILED_UNROLL)
         float r = shaped_reward(P, p, v, e0, steps);
         const bool goal = v.dg2 < P.goal_r2;
         const bool tout = steps > P.max_steps;
-        if (coll) r += P.reward_collision;
-        if (goal) r += P.reward_goal;
+        // game.py:279-284 (Q9): both bonuses can fall on one step; summed first so that -1000 + 1000 does not
+        // round the shaped reward to the float32 spacing at 1000
+        r += (coll ? P.reward_collision : 0.0f) + (goal ? P.reward_goal : 0.0f);
         float ret = pa.ep_return + r;
         const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
                             : goal ? ACAS2D_OUTCOME_GOAL : 0;

@@ -178,3 +178,73 @@ def test_cuda_kernels(name):
     check_against_oracle(name, run_host(case, cls=Gpu), run_oracle(case))
     if name == "q13_out_of_map":
         assert run_host(case, cls=Gpu)[2] & FLAG_OOB
+
+
+# ------------------------------------------------------------------------------------------------ random states
+def random_states(B, n, seed):
+    """States far outside what episodes visit: anywhere within half a map around the map, any heading, intruder
+    speeds 100 .. 300, game.steps 1 .. 1000, unclipped actions in [-2, 2]."""
+    rng = np.random.default_rng(seed)
+    player = np.stack([rng.uniform(-800, 2400, B), rng.uniform(-500, 1500, B), rng.uniform(0, 360, B)], 1)
+    traffic = np.stack([rng.uniform(-800, 2400, (B, n)), rng.uniform(-500, 1500, (B, n)),
+                        rng.uniform(100, 300, (B, n)), rng.uniform(0, 360, (B, n))], 2)
+    steps = rng.integers(1, 1001, B).astype(np.int32)
+    actions = rng.uniform(-2, 2, B).astype(np.float32)
+    return player, traffic, steps, actions
+
+
+def compare_random_step(got_obs, got_rew, got_flags, got_outcome, orc, player, traffic, steps, actions):
+    B, n = traffic.shape[:2]
+    st = orc.new_state(B)
+    st["player"][:, 0], st["player"][:, 1], st["player"][:, 2], st["player"][:, 3] = player[:, 0], player[:, 1], 200.0, player[:, 2]
+    st["traffic"][:] = traffic
+    st["steps"][:] = steps
+    with np.errstate(all="ignore"):
+        obs, rew, flags, outcome = orc.step(st, actions.astype(np.float64))
+    assert np.array_equal(got_flags & 15, flags & 15)                        # collision / goal / timeout / done: bit-exact
+    done = (flags & FLAG_DONE) > 0
+    assert np.array_equal(got_outcome[done], outcome[done])
+    g = np.asarray(got_obs, np.float64)
+    d = np.abs(g[:, :5] - obs[:, :5])
+    for c in (1, 4):
+        d[:, c] = np.minimum(d[:, c], 1.0 - d[:, c])
+    assert d.max() < parity.TOL_OBS_BASE
+    assert np.abs(g[:, 5::3] - obs[:, 5::3]).max() < parity.TOL_OBS_SEP
+    # float32 outputs: d_cpa is unbounded for near-parallel tracks, so its tolerance is relative beyond 1
+    cpa, rcpa = g[:, 6::3], obs[:, 6::3]
+    assert np.array_equal(np.isnan(cpa), np.isnan(rcpa))
+    with np.errstate(invalid="ignore"):
+        ok = np.abs(cpa - rcpa) <= parity.TOL_OBS_CPA * np.maximum(1.0, np.abs(rcpa))
+        flip = np.abs(np.abs(cpa) - np.abs(rcpa)) <= parity.TOL_OBS_CPA * np.maximum(1.0, np.abs(rcpa))    # Q12 sign flip
+    assert (ok | flip | np.isnan(rcpa)).all() and (~ok & flip).sum() <= 2
+    assert np.nanmax(np.abs(g[:, 7::3] - obs[:, 7::3])) < parity.TOL_OBS_VC
+    near_branch = (np.abs(obs[:, 7]) < 1e-6) | ~ok[:, 0]
+    dr = np.abs(np.asarray(got_rew, np.float64) - rew)
+    assert (dr[~near_branch] <= parity.TOL_REWARD_ABS + 1e-6 * np.abs(rew[~near_branch])).all(), dr[~near_branch].max()
+    assert done.mean() > 0.01 and (flags & FLAG_COLLISION > 0).mean() > 0.001
+
+
+@pytest.mark.parametrize("n,variant", [(1, 0), (1, 1), (5, 1)])
+def test_random_states_single_step_product_source(n, variant):
+    B = 20000
+    player, traffic, steps, actions = random_states(B, n, seed=100 + n)
+    hb = HostBatch(B, n, auto_reset=False, variant=variant)
+    hb.inject_state(player, traffic, steps, np.zeros(B))
+    obs, rew, done = hb.step(actions)
+    compare_random_step(obs, rew, hb.flags, hb.outcome, Oracle(n), player, traffic, steps, actions)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 5, 64])
+def test_random_states_single_step_cuda(n):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import BatchedACAS2D
+    B = 256 * 300 + 77 if n < 64 else 8192 + 3
+    player, traffic, steps, actions = random_states(B, n, seed=100 + n)
+    env = BatchedACAS2D(B, n_traffic=n, device="cuda:0", auto_reset=False)
+    env.inject_state(player, traffic, steps, np.zeros(B))
+    obs, rew, done = env.step(torch.from_numpy(actions).cuda())
+    c = lambda t: t.detach().cpu().numpy()      # noqa: E731
+    compare_random_step(c(obs), c(rew), c(env.flags), c(env.outcome), Oracle(n), player, traffic, steps, actions)
