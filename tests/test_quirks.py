@@ -248,3 +248,97 @@ def test_random_states_single_step_cuda(n):
     obs, rew, done = env.step(torch.from_numpy(actions).cuda())
     c = lambda t: t.detach().cpu().numpy()      # noqa: E731
     compare_random_step(c(obs), c(rew), c(env.flags), c(env.outcome), Oracle(n), player, traffic, steps, actions)
+
+
+# ------------------------------------------------------------------------------------------------ other settings
+# Every constant of settings.py the path reads, moved away from its default (a1: settings -> kernel parameters,
+# including the derived normalisers of game.py:120-128 and the reward constants of rewards.py).
+OTHER_SETTINGS = dict(WIDTH=1200, HEIGHT=800, FPS=50, MAX_STEPS=300, AIRCRAFT_SIZE=20, COLLISION_RADIUS=30,
+                      GOAL_RADIUS=100, SAFE_DISTANCE=150, AIRSPEED=150, AIRSPEED_FACTOR_MIN=0.8,
+                      AIRSPEED_FACTOR_MAX=1.25, ACC_LAT_LIMIT=120.0, PLAYER_INITIAL_HEADING_LIM=10,
+                      TRAFFIC_INITIAL_HEADING_LIM=40, REWARD_GOAL=500, REWARD_COLLISION=-750)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+def test_oracle_equals_the_unmodified_reference_under_other_settings():
+    import random
+    n = 2
+    ref_shim.load(n, **OTHER_SETTINGS)
+    try:
+        from gym_ACAS2D.envs.environment import ACAS2DEnv
+        orc = Oracle(n, **OTHER_SETTINGS)
+        random.seed(5)
+        arng = np.random.default_rng(5)
+        outcomes = []
+        with ref_shim.quiet(), np.errstate(all="ignore"):
+            env = ACAS2DEnv()
+            for ep in range(6):
+                obs = env.reset()
+                g = env.game
+                st = orc.new_state(1)
+                st["player"][0] = (g.player.x, g.player.y, g.player.v_air, g.player.psi, 0.0)
+                for i in range(n):
+                    t = g.traffic[i]
+                    st["traffic"][0, i] = (t.x, t.y, t.v_air, t.psi)
+                assert np.abs(orc.observe(st)[0] - obs).max() < 1e-14
+                for k in range(400):
+                    a = float(np.float32(arng.uniform(-1, 1))) * (0.2 if ep % 2 else 1.0)
+                    ro, rr, rd, _ = env.step(np.array([a]))
+                    co, cr, cf, coc = orc.step(st, np.array([a]))
+                    assert bool(cf[0] & FLAG_DONE) == rd
+                    assert np.nanmax(np.abs(ro - co[0])) < 1e-13 and abs(rr - cr[0]) < 1e-12 * max(1.0, abs(rr))
+                    if rd:
+                        assert g.outcome == coc[0] and g.steps == st["steps"][0]
+                        outcomes.append(int(coc[0]))
+                        break
+        assert len(outcomes) == 6                  # every episode ended within the 400 steps: MAX_STEPS = 300 took effect
+    finally:
+        ref_shim.unload()
+
+
+def _other_settings_rollout(make_env, to_np, B, n, steps):
+    seed, off = 41, 77
+    env = make_env(B, n, seed=seed, env_id_offset=off, auto_reset=True, **OTHER_SETTINGS)
+    orc = Oracle(n, **OTHER_SETTINGS)
+    st = orc.new_state(B)
+    orc.spawn_philox(st, seed, off)
+    assert np.abs(to_np(env.reset()) - orc.observe(st)).max() < parity.TOL_OBS_CPA
+    rng = np.random.default_rng(8)
+    rep = parity.ParityReport()
+    episodes = 0
+    for t in range(steps):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        obs, rew, done = env.step(a)
+        o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, a.astype(np.float64), seed, off)
+        d = f & FLAG_DONE > 0
+        assert np.array_equal(to_np(done).astype(bool), d)
+        parity.compare_step(rep, np.where(d[:, None], to_np(env.term_obs), to_np(obs)), to_np(rew), to_np(env.flags),
+                            np.where(d[:, None], term, o), r, f)
+        if d.any():
+            assert np.array_equal(to_np(env.outcome)[d], oc[d]) and np.array_equal(to_np(env.ep_length)[d], ep_len[d])
+            episodes += int(d.sum())
+    parity.assert_flags_exact(rep)
+    assert episodes > B                              # MAX_STEPS = 300: every env finished at least once
+
+
+@pytest.mark.parametrize("n,variant", [(1, 0), (3, 1)])
+def test_other_settings_product_source(n, variant):
+    _other_settings_rollout(lambda B, n, **kw: HostBatch(B, n, variant=variant, **kw), np.asarray, 48, n, 700)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 8])
+def test_other_settings_cuda(n):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from gym_ACAS2D.envs import BatchedACAS2D
+
+    class Gpu(BatchedACAS2D):
+        def __init__(self, B, n, **kw):
+            super().__init__(B, n_traffic=n, device="cuda:0", **kw)
+
+        def step(self, a):
+            return super().step(torch.from_numpy(np.asarray(a, np.float32)).cuda())
+
+    _other_settings_rollout(Gpu, lambda t: t.detach().cpu().numpy(), 256 * 2 + 9, n, 700)
