@@ -340,6 +340,13 @@ def run_ours(args):
             ms_f = timed(lambda k: env.rollout_random(fused_k, action_seed=1, step0=100 + fused_k * k), reps)
             other["fused_rollout_64_steps_per_launch"] = {"value": world * B * fused_k * reps / (ms_f * 1e-3), "unit": UNIT,
                                                           "note": "in-kernel Philox actions, state in registers, no per-step outputs"}
+            # open-loop K-step launches WITH every step's outputs (the caller holds the K actions): state traffic / K
+            ko, kr, kd = env.step_k(actions)
+            ms_k = timed(lambda k: env.step_k(actions, ko, kr, kd), 8)
+            other["step_k_%d_steps_per_launch_with_outputs" % KA] = {
+                "value": world * B * KA * 8 / (ms_k * 1e-3), "unit": UNIT, "us_per_env_step_batch": 1e3 * ms_k / (8 * KA),
+                "note": "acas2d_step_k: obs / reward / done of every step written, state read and written once per launch "
+                        "(80 / K + 41 bytes per env-step instead of 121)"}
             # closed-loop rollout: the reference's trained actor (8-64-64-1 tanh MLP) fused with the env step
             from gym_ACAS2D.policy import MlpActor
             fixture = os.path.join(ROOT, "tests", "golden", "ppo_policy_1048576_11.npz")

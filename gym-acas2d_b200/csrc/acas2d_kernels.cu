@@ -293,6 +293,30 @@ rollout_n1_kernel(const DevParams P, const StatePtrs S, int num_steps, uint64_t 
     tally_flush_warp(S.stats, tally);
 }
 
+// K consecutive steps per launch for callers that already hold all K actions (open loop: random-action
+// rollouts, replays of recorded action sequences).  State stays in registers between the steps -- per
+// env-step only the action is read and the step's outputs are written: (80 / K + 41) bytes instead of 121.
+__global__ void __launch_bounds__(kBlock)
+step_k_n1_kernel(const DevParams P, const StatePtrs S, const int num_steps, const float *__restrict__ actions,
+                 const Sinks out)
+{
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    Tally tally;
+    tally_clear(tally);
+    if (i < S.B) {
+        Env1 e;
+        load_env1(S, i, e, false);
+        Sinks o = out;
+        for (int k = 0; k < num_steps; ++k) {
+            const float a = __ldcs(actions + (int64_t)k * S.B + i);
+            step_env1<false, true>(P, S, e, a, i, o, tally, nullptr);
+            o.obs += 8 * S.B; o.reward += S.B; o.done += S.B;              // next step's [B] slice of the [K][B] outputs
+        }
+        store_env1(S, i, e, false);
+    }
+    tally_flush_warp(S.stats, tally);
+}
+
 // ---------------------------------------------------------------- N_TRAFFIC > 1 (first version)
 template <bool MINSEP>
 __global__ void __launch_bounds__(kBlock)
@@ -981,6 +1005,19 @@ int policy_prepare_device()
     return 0;
 }
 }  // namespace
+
+int acas2d_step_k(const acas2d_params *params, const acas2d_state *state, int32_t num_steps, const float *actions,
+                  float *obs, float *reward, uint8_t *done, const acas2d_step_aux *aux, void *stream)
+{
+    if (int e = check_args(params, state)) return e;
+    if (params->n_traffic != 1 || state->min_sep) return ACAS2D_E_BAD_TRAFFIC;
+    if (num_steps < 0) return ACAS2D_E_BAD_SIZE;
+    if (state->num_envs == 0 || num_steps == 0) return 0;
+    if (!actions || !obs || !reward || !done) return ACAS2D_E_NULL;
+    step_k_n1_kernel<<<grid_for(state->num_envs), kBlock, 0, (cudaStream_t)stream>>>(
+        make_dev_params(*params), make_state_ptrs(*state), num_steps, actions, make_sinks(obs, reward, done, aux));
+    return finish_launch();
+}
 
 int acas2d_policy_step(const acas2d_params *params, const acas2d_state *state, const float *weights,
                        float log_std, const float *obs_in, float *actions_out, float *logp_out, float *obs_out,

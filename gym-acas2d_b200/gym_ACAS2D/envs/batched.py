@@ -148,6 +148,26 @@ class BatchedACAS2D:
         self.launches += 1
         return self.obs, self.reward, self.done
 
+    def step_k(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
+               done: Optional[torch.Tensor] = None):
+        """K consecutive steps in one launch for actions known in advance (open loop): ``actions`` float32 [K, B]
+        -> (obs [K, B, L], reward [K, B], done bool [K, B]), bit-identical to K ``step`` calls; the state is
+        read and written once per launch instead of once per step (N_TRAFFIC == 1)."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        assert a.dim() == 2 and a.shape[1] == self.num_envs
+        K, B, L, dev = a.shape[0], self.num_envs, self.obs_dim, self.device
+        obs = torch.empty(K, B, L, dtype=torch.float32, device=dev) if obs is None else obs
+        reward = torch.empty(K, B, dtype=torch.float32, device=dev) if reward is None else reward
+        done = torch.empty(K, B, dtype=torch.uint8, device=dev) if done is None else done
+        with torch.cuda.device(dev):
+            _native.check(self.lib.acas2d_step_k(self._p(), self._s(), K, a.data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                                                 done.data_ptr(), ctypes.byref(self._aux_lean), self._stream()),
+                          "acas2d_step_k")
+        self.launches += 1
+        if K:
+            self.obs.copy_(obs[K - 1]); self.reward.copy_(reward[K - 1]); self.done_u8.copy_(done[K - 1])
+        return obs, reward, done.view(torch.bool)
+
     def host_buffers(self) -> Dict[str, np.ndarray]:
         """Pinned host staging buffers of ``step_host`` as numpy views: ``actions`` float32[B] (write
         your actions here and call ``step_host()`` to skip the pageable->pinned copy), ``obs``,

@@ -183,6 +183,15 @@ int acas2d_observe(const acas2d_params *params, const acas2d_state *state, float
  * ACAS2DGame.view() (game.py:323-347) without sprites and HUD text.  Not part of the hot path. */
 int acas2d_render(const acas2d_params *params, const acas2d_state *state, int64_t env_index, uint8_t *rgb, void *stream);
 
+/* num_steps consecutive steps in ONE launch, for callers that already hold the actions of all of them (open
+ * loop: random-action rollouts, replays of recorded action sequences; N_TRAFFIC == 1, no min_sep tracking).
+ * actions float[K][B]; obs float[K][B][L], reward float[K][B], done uint8[K][B] receive every step's outputs
+ * exactly as K calls of acas2d_step would write them (bit-identical, auto-reset included); the [B]-shaped aux
+ * arrays are overwritten by each step (the last finished episode per env stays).  The state is read and
+ * written once per launch instead of once per step. */
+int acas2d_step_k(const acas2d_params *params, const acas2d_state *state, int32_t num_steps, const float *actions,
+                  float *obs, float *reward, uint8_t *done, const acas2d_step_aux *aux, void *stream);
+
 /* Synthetic benchmark path: K consecutive auto-resetting steps per launch with actions
  * drawn in-kernel, a ~ U(-1,1) from Philox(key = action_seed, counter = (global env id,
  * step0 + k)).  State stays in registers between the K steps; nothing but the state, the

@@ -602,3 +602,26 @@ def test_unequal_speeds_q3_on_the_gpu(cuda, n):
                             np.where(d[:, None], term, o), r, f)
     parity.assert_flags_exact(rep)
     assert rep.steps == 400 * B
+
+
+def test_step_k_equals_k_single_steps(cuda):
+    """acas2d_step_k (K open-loop steps per launch, state in registers in between) writes exactly what K calls
+    of acas2d_step write -- every step's obs / reward / done, the state, the episode counters -- with
+    auto-reset inside the window."""
+    B, K = 256 * 5 + 19, 12
+    a, b = make(B, seed=4, auto_reset=True), make(B, seed=4, auto_reset=True)
+    for env in (a, b):
+        env.reset()
+        ex = env.extract_state(); ex["steps"][:] = 985 + (np.arange(B) % 14)          # plenty of timeouts inside the window
+        env.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    for rep in range(3):
+        acts = torch.stack([a.random_actions(rep * K + k, action_seed=9) for k in range(K)])
+        obs_k, rew_k, done_k = a.step_k(acts)
+        for k in range(K):
+            o, r, d = b.step(acts[k], full_outputs=False)
+            assert torch.equal(obs_k[k], o) and torch.equal(rew_k[k], r) and torch.equal(done_k[k], d), (rep, k)
+        assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.thot, b.thot)
+        assert torch.equal(a.episode_idx, b.episode_idx) and torch.equal(a.episode_counters(), b.episode_counters())
+        assert torch.equal(a.obs, b.obs)
+    assert int(a.episode_counters()[0]) >= B
+    assert a.step_k(acts[:0])[0].shape[0] == 0                                          # K = 0: nothing to do
