@@ -341,12 +341,19 @@ def run_ours(args):
             other["fused_rollout_64_steps_per_launch"] = {"value": world * B * fused_k * reps / (ms_f * 1e-3), "unit": UNIT,
                                                           "note": "in-kernel Philox actions, state in registers, no per-step outputs"}
             # open-loop K-step launches WITH every step's outputs (the caller holds the K actions): state traffic / K
+            import ctypes
             ko, kr, kd = env.step_k(actions)
-            ms_k = timed(lambda k: env.step_k(actions, ko, kr, kd), 8)
+            kd8 = kd.view(torch.uint8)
+            step_k_raw = lambda k: lib.acas2d_step_k(env._p(), env._s(), KA, actions.data_ptr(), ko.data_ptr(), kr.data_ptr(),   # noqa: E731
+                                                     kd8.data_ptr(), ctypes.byref(env._aux_lean), torch.cuda.current_stream().cuda_stream)
+            for k in range(2):
+                step_k_raw(k)
+            ms_k = timed(step_k_raw, 8)
             other["step_k_%d_steps_per_launch_with_outputs" % KA] = {
                 "value": world * B * KA * 8 / (ms_k * 1e-3), "unit": UNIT, "us_per_env_step_batch": 1e3 * ms_k / (8 * KA),
-                "note": "acas2d_step_k: obs / reward / done of every step written, state read and written once per launch "
-                        "(80 / K + 41 bytes per env-step instead of 121)"}
+                "note": "acas2d_step_k (C-ABI call, kernel only): obs / reward / done of every step written, state read and "
+                        "written once per launch (80 / K + 41 bytes per env-step instead of 121)"}
+            del ko, kr, kd, kd8
             # closed-loop rollout: the reference's trained actor (8-64-64-1 tanh MLP) fused with the env step
             from gym_ACAS2D.policy import MlpActor
             fixture = os.path.join(ROOT, "tests", "golden", "ppo_policy_1048576_11.npz")

@@ -307,10 +307,13 @@ step_k_n1_kernel(const DevParams P, const StatePtrs S, const int num_steps, cons
         Env1 e;
         load_env1(S, i, e, false);
         Sinks o = out;
+        float a = __ldcs(actions + i);
         for (int k = 0; k < num_steps; ++k) {
-            const float a = __ldcs(actions + (int64_t)k * S.B + i);
+            // the next step's action is in flight while this step's ~400-instruction chain runs
+            const float a_next = (k + 1 < num_steps) ? __ldcs(actions + (int64_t)(k + 1) * S.B + i) : 0.0f;
             step_env1<false, true>(P, S, e, a, i, o, tally, nullptr);
             o.obs += 8 * S.B; o.reward += S.B; o.done += S.B;              // next step's [B] slice of the [K][B] outputs
+            a = a_next;
         }
         store_env1(S, i, e, false);
     }
