@@ -253,6 +253,16 @@ class FusedLearner:
     def sb3_state_dict(self) -> Dict[str, torch.Tensor]:
         return {k: v.clone() for k, v in unpack_params(self.params).items()}
 
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Checkpoint of the learner: parameter block, Adam moments and step count (same keys as ``TorchLearner``)."""
+        return dict(params=self.params.detach().clone(), adam_m=self.adam_m.clone(), adam_v=self.adam_v.clone(),
+                    adam_step=self.adam_step.clone().to(torch.int64))
+
+    def load_state_dict(self, d: Dict[str, torch.Tensor]) -> None:
+        """Resume in place (captured graphs stay valid: the storages do not move)."""
+        self.params.copy_(d["params"]); self.adam_m.copy_(d["adam_m"]); self.adam_v.copy_(d["adam_v"])
+        self.adam_step.copy_(d["adam_step"].to(torch.int32))
+
     # ---- value head and GAE
     def values(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         obs = obs.reshape(-1, OBS_DIM)
@@ -381,6 +391,24 @@ class TorchLearner:
 
     def sb3_state_dict(self):
         return {k: v.detach().clone() for k, v in unpack_params(self.params).items()}
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Checkpoint with the keys of ``FusedLearner.state_dict`` (the two learners can resume each other)."""
+        st = self.opt.state.get(self.params, {})
+        zeros = torch.zeros_like(self.params.detach())
+        step = st.get("step", torch.zeros(()))
+        return dict(params=self.params.detach().clone(), adam_m=st.get("exp_avg", zeros).clone(),
+                    adam_v=st.get("exp_avg_sq", zeros).clone(),
+                    adam_step=torch.as_tensor(step).detach().reshape(1).to(torch.int64).cpu())
+
+    def load_state_dict(self, d: Dict[str, torch.Tensor]) -> None:
+        with torch.no_grad():
+            self.params.copy_(d["params"])
+        capturable = self.device.type == "cuda"
+        step = d["adam_step"].reshape(()).to(torch.float32)
+        self.opt.state[self.params] = dict(step=step.to(self.device) if capturable else step.cpu(),
+                                           exp_avg=d["adam_m"].to(self.device).clone(),
+                                           exp_avg_sq=d["adam_v"].to(self.device).clone())
 
     def values(self, obs, out=None):
         with torch.no_grad():

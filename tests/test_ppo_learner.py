@@ -118,6 +118,25 @@ def test_data_parallel_gradient_exchange_world_size_2_gloo(tmp_path):
     assert out.stdout.count("ok") == 2
 
 
+def test_learner_checkpoint_resume_cpu():
+    """Checkpoint / resume of the learner (parameter block, Adam moments, step count): a resumed learner continues
+    exactly like the one that never stopped (torch learner on the CPU; the CUDA learner shares the keys)."""
+    cfg = PpoConfig.sb3_defaults()
+    data = synthetic_rollout(2048, seed=4)
+    a = ppo.TorchLearner("cpu", cfg, init_state_dict(), cuda_graph=False)
+    for _ in range(5):
+        a.gradient(*data, None); a.apply(1.0)
+    ckpt = {k: v.clone() for k, v in a.state_dict().items()}
+    assert int(ckpt["adam_step"]) == 5 and ckpt["params"].numel() == _native.PPO_PARAM_FLOATS
+    b = ppo.TorchLearner("cpu", cfg, init_state_dict(seed=99), cuda_graph=False)
+    b.load_state_dict(ckpt)
+    for L in (a, b):
+        for _ in range(4):
+            L.gradient(*data, None); L.apply(1.0)
+    assert torch.equal(a.params.detach(), b.params.detach())
+    assert int(b.state_dict()["adam_step"]) == 9
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _group_errors(got: torch.Tensor, ref: torch.Tensor):
     """max |got - ref| per tensor of the block, relative to that tensor's largest reference entry."""
@@ -277,6 +296,30 @@ def test_graphed_rollout_equals_eager_rollout_while_the_policy_changes():
     assert not torch.equal(out[0][0][0]["actions"], out[0][0][1]["actions"])
     std0 = float((out[0][0][0]["logp"]).mean()); std1 = float((out[0][0][1]["logp"]).mean())
     assert std1 > std0 + 0.2                                         # smaller log_std -> larger log-densities: it was read live
+
+
+@pytest.mark.gpu
+def test_learner_checkpoint_resume_across_learners():
+    """A FusedLearner checkpoint resumes a FusedLearner bit for bit, and a TorchLearner to within rounding."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    dev = "cuda:0"
+    cfg = PpoConfig.sb3_defaults()
+    data = synthetic_rollout(4096, seed=6, device=dev)
+    a = ppo.FusedLearner(dev, cfg, init_state_dict(), cuda_graph=False)
+    for _ in range(5):
+        a.step(*data, None, 4096)
+    ckpt = a.state_dict()
+    assert int(ckpt["adam_step"]) == 5
+    b = ppo.FusedLearner(dev, cfg, init_state_dict(seed=99), cuda_graph=False)
+    b.load_state_dict(ckpt)
+    t = ppo.TorchLearner(dev, cfg, init_state_dict(seed=98), cuda_graph=False)
+    t.load_state_dict(ckpt)
+    for _ in range(4):
+        a.step(*data, None, 4096); b.step(*data, None, 4096)
+        t.gradient(*data, None); t.apply(1.0)
+    assert torch.equal(a.params, b.params) and int(b.adam_step) == 9
+    assert float((t.params.detach() - a.params).abs().max()) < 2e-5
 
 
 @pytest.mark.gpu
