@@ -159,6 +159,8 @@ class BatchedACAS2D:
         obs = torch.empty(K, B, L, dtype=torch.float32, device=dev) if obs is None else obs
         reward = torch.empty(K, B, dtype=torch.float32, device=dev) if reward is None else reward
         done = torch.empty(K, B, dtype=torch.uint8, device=dev) if done is None else done
+        if done.dtype == torch.bool:                       # the buffer this method returned earlier, passed back in
+            done = done.view(torch.uint8)
         with torch.cuda.device(dev):
             _native.check(self.lib.acas2d_step_k(self._p(), self._s(), K, a.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                                                  done.data_ptr(), ctypes.byref(self._aux_lean), self._stream()),
