@@ -1,11 +1,12 @@
 """TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-Imports the UNMODIFIED reference (``/root/reference/gym_ACAS2D``) in the build
-container under in-process stand-ins for ``gym`` and ``pygame`` (neither is
-installed).  Every arithmetic line of the reference then
-runs verbatim.  The reference tree does not exist on the GPU box, so this module
-is used only by ``tests/golden/make_golden.py`` (fixture generation) and by the
-CPU tests that cross-check the C oracle when the tree is present.
+Imports the UNMODIFIED reference (``/root/reference/gym_ACAS2D``, or its hot-path
+files copied byte for byte into the git-ignored ``oracle/_ref`` by
+``oracle/make_ref.py``) under in-process stand-ins for ``gym`` and ``pygame``
+(neither is installed).  Every arithmetic line of the
+reference then runs verbatim.  Used by ``tests/golden/make_golden.py`` (fixture
+generation), by the CPU tests that cross-check the C oracle, and by
+``oracle/ref_runner.py`` (the CPU arm of ``bench.py``: ``kind: "reference"``).
 """
 from __future__ import annotations
 
@@ -16,11 +17,29 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ACAS2D_REFERENCE_ROOT", "/root/reference")
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/make_ref.py (git-ignored)
+
+
+def _find_root() -> str:
+    """The reference checkout when it is there (build container), else the unmodified copy of its
+    hot-path files that ``oracle/make_ref.py`` placed in ``oracle/_ref`` (travels to the GPU box)."""
+    for root in (os.environ.get("ACAS2D_REFERENCE_ROOT"), "/root/reference", _LOCAL_COPY):
+        if root and os.path.isdir(os.path.join(root, "gym_ACAS2D", "envs")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_ACAS2D", "envs"))
+
+
+def full_tree() -> bool:
+    """True when the whole reference checkout (golden CSV, model zips, notebooks) is present, not just
+    the hot-path source files of ``oracle/_ref``."""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_ACAS2D", "models"))
 
 
 def _stub_modules():

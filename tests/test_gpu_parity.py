@@ -158,6 +158,60 @@ def test_traffic_sweep_vs_oracle(cuda, n, B, T):
     assert np.abs(ex["traffic"][:, :, :2] - st["traffic"][:, :, :2]).max() < parity.TOL_POS
 
 
+@pytest.mark.parametrize("n,T", [(8, 60), (64, 40), (256, 24)])
+def test_config4_parity_at_stated_batch(cuda, n, T):
+    """BASELINE config 4 AT ITS STATED BATCH: 65 536 envs, N_TRAFFIC = 8 / 64 / 256, auto-reset, random actions.
+    Eight 64-env windows spread over the batch (first / last warps and CTAs, odd offsets) are stepped by the
+    oracle with the same global env ids: flags bit-exact, floats within the stated tolerances.  The lean
+    launch the benchmark times (no flags / terminal rows) must agree with the full one bit for bit over
+    the WHOLE batch (reference per-intruder loop: game.py:185-189,205-210)."""
+    B, seed, W = 65536, 11, 64
+    full = make(B, n, seed=seed, auto_reset=True)
+    lean = make(B, n, seed=seed, auto_reset=True)
+    o_full = full.reset().clone()
+    assert torch.equal(o_full.view(torch.int32), lean.reset().view(torch.int32))
+    offsets = [0, 64, 4096 - 32, 20000 + 7, 32768 - 16, 40001, 65536 - 128 - 3, 65536 - 64]
+    orc = Oracle(n)
+    states = []
+    for off in offsets:
+        st = orc.new_state(W)
+        orc.spawn_philox(st, seed, off)
+        ref0 = orc.observe(st)
+        assert np.nanmax(np.abs(npy(o_full[off:off + W]) - ref0)) < parity.TOL_OBS_CPA
+        states.append(st)
+    rep = parity.ParityReport()
+    episodes = 0
+    for t in range(T):
+        a = full.random_actions(t, action_seed=9)
+        of, rf, df = full.step(a)
+        ol, rl, dl = lean.step(a, full_outputs=False)
+        assert torch.equal(of.view(torch.int32), ol.view(torch.int32))
+        assert torch.equal(rf.view(torch.int32), rl.view(torch.int32)) and torch.equal(df, dl)
+        a_n, of_n, rf_n, ff_n, tf_n = npy(a), npy(of), npy(rf), npy(full.flags), npy(full.term_obs)
+        for off, st in zip(offsets, states):
+            sl = slice(off, off + W)
+            o, r, f, oc, term, ep_ret, ep_len = orc.vec_step(st, a_n[sl].astype(np.float64), seed, off)
+            dn = f & FLAG_DONE > 0
+            assert np.array_equal(npy(df[sl]), dn)
+            parity.compare_step(rep, np.where(dn[:, None], tf_n[sl], of_n[sl]), rf_n[sl], ff_n[sl],
+                                np.where(dn[:, None], term, o), r, f)
+            if dn.any():
+                assert np.nanmax(np.abs(of_n[sl][dn] - o[dn])) < parity.TOL_OBS_CPA
+                assert np.array_equal(npy(full.ep_length[sl])[dn], ep_len[dn])
+                assert np.array_equal(npy(full.outcome[sl])[dn], oc[dn])
+                episodes += int(dn.sum())
+    assert rep.flag_mismatch == 0 and rep.steps == T * W * len(offsets), rep
+    assert torch.equal(full.ppos, lean.ppos) and torch.equal(full.paux, lean.paux) and torch.equal(full.thot, lean.thot)
+    assert torch.equal(full.episode_counters(), lean.episode_counters())
+    ex = full.extract_state()
+    for off, st in zip(offsets, states):
+        assert np.array_equal(ex["episode_idx"][off:off + W], st["episode_idx"] + 1)
+        assert np.abs(ex["traffic"][off:off + W, :, :2] - st["traffic"][:, :, :2]).max() < parity.TOL_POS
+        assert np.abs(ex["player"][off:off + W] - st["player"][:, [0, 1, 3]]).max() < parity.TOL_POS
+    assert episodes > (0 if n == 8 else 100)
+    print(rep)
+
+
 @pytest.mark.parametrize("n", [2, 3, 8, 12, 16, 24, 64, 96, 256])
 def test_tiled_kernel_equals_loop_kernel(cuda, n):
     """The shared-memory tiled kernel (G lanes per env, cp.async staging, shuffle reductions) and the
