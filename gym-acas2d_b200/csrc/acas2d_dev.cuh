@@ -91,4 +91,26 @@ __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gmem_
 #endif
 }
 
+// Same without a cache hint (data that is re-read by the next step and fits L2).
+__device__ __forceinline__ void tma_load_1d_plain(uint32_t smem_dst, const void *gmem_src, unsigned bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// 1-D TMA bulk copy shared -> global (bytes % 16 == 0, both addresses 16-byte aligned), then wait until the
+// shared source has been read.  The caller orders its generic-proxy shared writes before this with
+// fence.proxy.async + a barrier.
+__device__ __forceinline__ void tma_store_1d_and_wait(void *gmem_dst, uint32_t smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_shared()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 }  // namespace acas2d

@@ -41,7 +41,12 @@ struct alignas(16) Float4 { float x, y, z, w; };
 struct alignas(32) Residual { double x0, y0, psi, v; };
 
 constexpr int32_t kResidualBit = ACAS2D_STEPS_RESIDUAL_BIT;
-constexpr int32_t kStepsMask = ACAS2D_STEPS_RESIDUAL_BIT - 1;
+constexpr int32_t kCompactBit = ACAS2D_STEPS_COMPACT_BIT;   // the env's fast-path records (tkin / tpsi0) describe it exactly
+constexpr int32_t kDownBit = ACAS2D_STEPS_DOWN_BIT;
+constexpr int32_t kStepsMask = ACAS2D_STEPS_MASK;
+
+// Kinematic cache of one intruder (acas2d_b200.h "tkin"): origin (float32-exact) and displacement per step.
+struct alignas(8) TrafficKin { float x0, y0; double dx, dy; };
 
 struct StatePtrs {
     Vec2d *ppos;
@@ -54,6 +59,9 @@ struct StatePtrs {
     uint64_t seed;
     uint64_t gid0;
     int64_t B;
+    TrafficKin *tkin;       // optional (N > 1)
+    float *tpsi0;           // optional (N == 1)
+    Float4 *pstage;         // optional scratch (N > 1): [7][B] 16-byte words
 };
 
 struct Sinks {
@@ -114,6 +122,7 @@ inline DevParams make_dev_params(const acas2d_params &p)
     d.n_traffic = p.n_traffic;
     d.max_steps = (int32_t)p.max_steps;
     d.auto_reset = p.auto_reset;
+    d.q3_trivial = (p.airspeed_factor_min == 1.0 && p.airspeed_factor_max == 1.0) ? 1 : 0;
     return d;
 }
 
@@ -130,6 +139,9 @@ inline StatePtrs make_state_ptrs(const acas2d_state &s)
     o.seed = s.seed;
     o.gid0 = s.env_id_offset;
     o.B = s.num_envs;
+    o.tkin = (TrafficKin *)s.tkin;
+    o.tpsi0 = s.tpsi0;
+    o.pstage = (Float4 *)s.pstage;
     return o;
 }
 
@@ -196,10 +208,41 @@ ACAS_HD Intruder intruder_at(const DevParams &P, const TrafficRec &t, double k)
     sincos_deg(t.psi, &s, &c);
     it.dx = (t.v * c) * P.dt;                                           // aircraft.py:25-26 with a_lat = 0
     it.dy = (t.v * s) * P.dt;
-    it.x = t.x0 + k * it.dx;
-    it.y = t.y0 + k * it.dy;
+    it.x = fma(k, it.dx, t.x0);
+    it.y = fma(k, it.dy, t.y0);
     it.dyq = (P.airspeed * s) * P.dt;                                   // Q3 (no division: the player's speed times the sine)
     return it;
+}
+
+// The same intruder from its kinematic cache: no sin / cos (the cached dx, dy are the values intruder_at
+// derives, bit for bit).  Only for envs carrying kCompactBit: float32-exact origin, speed == AIRSPEED (Q3 trivial).
+ACAS_HD Intruder intruder_from_kin(const TrafficKin &q, double k)
+{
+    Intruder it;
+    it.dx = q.dx; it.dy = q.dy; it.dyq = q.dy;
+    it.x = fma(k, q.dx, (double)q.x0);
+    it.y = fma(k, q.dy, (double)q.y0);
+    return it;
+}
+
+ACAS_HD void kin_store(const StatePtrs &S, int64_t ij, const TrafficRec &t, const Intruder &it)
+{
+    if (S.tkin == nullptr) return;
+    TrafficKin q;
+    q.x0 = (float)t.x0; q.y0 = (float)t.y0; q.dx = it.dx; q.dy = it.dy;
+    S.tkin[ij] = q;
+}
+
+// May this intruder use the fast-path records?  (float32-exact record AND flying at exactly AIRSPEED.)
+ACAS_HD bool traffic_is_plain(const DevParams &P, const TrafficRec &t, bool needs_residual)
+{
+    return !needs_residual && t.v == P.airspeed;
+}
+
+// Flag bits of paux.steps for a freshly spawned env with N > 1 (the N == 1 kernels set theirs in step_env1).
+ACAS_HD int32_t spawn_bits(const DevParams &P, const StatePtrs &S)
+{
+    return (S.tkin != nullptr && P.q3_trivial && P.n_traffic > 1) ? kCompactBit : 0;
 }
 
 // Spawn of intruder j of (gid, episode), rounded to float32 (game.py:97-114).
@@ -415,7 +458,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
                                  (tout ? ACAS2D_FLAG_TIMEOUT : 0) | (done ? ACAS2D_FLAG_DONE : 0) |
                                  (oob ? ACAS2D_FLAG_OOB : 0));
     }
-    int steps_out = steps | (residual ? kResidualBit : 0);
+    int steps_out = steps | (pa.steps & ~kStepsMask);
     if (done) {
         if (out.outcome) out.outcome[i] = (uint8_t)outcome;
         if (out.ep_return) out.ep_return[i] = ret;
@@ -439,13 +482,15 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             for (int j = 0; j < N; ++j) {
                 const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
                 traffic_store(S, i * N + j, tr, false);
-                const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
+                const Intruder it = intruder_at(P, tr, 0.0);
+                kin_store(S, i * N + j, tr, it);
+                const Encounter en = encounter(P, p, it);
                 minsep = fminf(minsep, en.d);
                 row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
                 row[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
                 row[5 + 3 * j + 2] = en.v_c * P.vc_scale;
             }
-            steps_out = 1;
+            steps_out = 1 | spawn_bits(P, S);
             ret = 0.0f;
         }
     }
@@ -476,7 +521,9 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     for (int j = 0; j < N; ++j) {
         const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
         traffic_store(S, i * N + j, tr, false);
-        const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
+        const Intruder it = intruder_at(P, tr, 0.0);
+        kin_store(S, i * N + j, tr, it);
+        const Encounter en = encounter(P, p, it);
         minsep = fminf(minsep, en.d);
         if (row) {
             row[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
@@ -485,7 +532,7 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
         }
     }
     Vec2d np; np.x = p.x; np.y = p.y;
-    PlayerAux na; na.psi = p.psi; na.steps = 1; na.ep_return = 0.0f;
+    PlayerAux na; na.psi = p.psi; na.steps = 1 | spawn_bits(P, S); na.ep_return = 0.0f;
     S.ppos[i] = np;
     S.paux[i] = na;
     if (S.min_sep) S.min_sep[i] = minsep;
@@ -524,21 +571,24 @@ ACAS_HD void inject_env(const DevParams &P, const StatePtrs &S, int64_t i, const
     const int st = steps[i] & kStepsMask;
     float minsep = INFINITY;
     const double back = (double)(st - 1);
-    bool residual = false;
+    bool residual = false, plain = S.tkin != nullptr;
     for (int j = 0; j < N; ++j) {
         const int64_t ij = i * N + j;
         TrafficRec tr;
         const double x = traffic[4 * ij], y = traffic[4 * ij + 1];
         tr.v = traffic[4 * ij + 2]; tr.psi = traffic[4 * ij + 3];
-        double dx, dy;
-        heading_to_velocity(P, tr.v, tr.psi, &dx, &dy);
-        tr.x0 = x - back * dx; tr.y0 = y - back * dy;               // closed-form origin (steps == 1)
-        residual |= traffic_store(S, ij, tr, true);
+        tr.x0 = x; tr.y0 = y;
+        const Intruder it = intruder_at(P, tr, 0.0);                // displacement per step (dx, dy)
+        tr.x0 = x - back * it.dx; tr.y0 = y - back * it.dy;         // closed-form origin (steps == 1)
+        const bool need = traffic_store(S, ij, tr, true);
+        kin_store(S, ij, tr, it);
+        residual |= need;
+        plain = plain && traffic_is_plain(P, tr, need);
         const double ox = x - np.x, oy = y - np.y;
         minsep = fminf(minsep, sqrtf((float)(ox * ox + oy * oy)));
     }
     PlayerAux na; na.psi = player[3 * i + 2]; na.ep_return = (float)total_reward[i];
-    na.steps = st | (residual ? kResidualBit : 0);
+    na.steps = st | (residual ? kResidualBit : 0) | ((plain && N > 1) ? kCompactBit : 0);
     S.ppos[i] = np;
     S.paux[i] = na;
     if (S.min_sep) S.min_sep[i] = minsep;

@@ -30,6 +30,7 @@
 #include "../../include/acas2d_b200.h"
 #include "acas2d_env.cuh"
 #include "acas2d_dev.cuh"
+#include "acas2d_tiled.cuh"
 #include "acas2d_policy_tc.cuh"
 #include "acas2d_ppo.cuh"
 
@@ -332,319 +333,69 @@ step_loop_kernel(const DevParams P, const StatePtrs S, const float *__restrict__
     tally_flush_warp(S.stats, tally);
 }
 
-// ---------------------------------------------------------------- N_TRAFFIC > 1: shared-memory tiled
-// G lanes cooperate on one env (G = 1, 2, ..., 32; G divides N), so a warp owns E = 32/G
-// consecutive envs and every lane handles N/G intruders (about eight: the instruction budget of an
-// HBM-bound step does not allow a whole warp per env below N = 256).
-//   1. the warp's traffic tile -- E*N float4 records, contiguous in HBM -- is staged into shared
-//      memory with coalesced 16-byte cp.async copies while the player update runs;
-//   2. each lane walks its intruders (rotated start, so the 16-byte shared loads of a quarter warp
-//      fall in distinct banks), keeps collision / min-separation partials in registers and writes
-//      the three observation entries of each intruder into the warp's observation tile;
-//   3. any-collision and min-separation are reduced over the G lanes with xor shuffles;
-//   4. lane 0 of each group finishes reward / flags / episode bookkeeping;
-//   5. finished envs respawn cooperatively (one Philox block per intruder) and re-observe;
-//   6. the observation tile is written back row by row, fully coalesced.
-constexpr int kTiledWarps = 4;
-
-// Shared-memory geometry of one warp: traffic tile of E rows x TS float4 (TS = N + 1 for G == 1 so
-// that the 16-byte reads of a quarter warp, one row per lane, fall in distinct banks; TS = N
-// otherwise, where a rotated start does the same job), then E unpadded observation rows.
-__host__ __device__ inline int tiled_row_stride(int N, int G) { return G == 1 ? N + 1 : N; }
-
-inline size_t tiled_warp_bytes(int N, int G)
+// Intruders per lane the group size aims at.  Round 1 (player update redone by every lane of a group): 2 per lane
+// 0.43 / 0.38 / 0.36 / 0.30 of the roofline at N = 8 / 16 / 32 / 64, 4: 0.60 / 0.53 / 0.50 / 0.42, 8: 0.71 / 0.66 /
+// 0.63 / 0.52, 16: 0.70 / 0.51 / 0.49 / 0.40.  Runtime knob (acas2d_set_tiled_tuning / ACAS2D_TILED_PER_LANE).
+int &tiled_per_lane()
 {
-    const int E = 32 / G, L = 5 + 3 * N;
-    return (size_t)E * tiled_row_stride(N, G) * 16 + (((size_t)E * L * 4 + 15) & ~(size_t)15);
+    static int v = [] {
+        const char *e = std::getenv("ACAS2D_TILED_PER_LANE");
+        const int x = e ? std::atoi(e) : 0;
+        return (x >= 1 && x <= 64) ? x : 8;
+    }();
+    return v;
 }
 
-inline size_t tiled_smem_bytes(int N, int G) { return kTiledWarps * tiled_warp_bytes(N, G); }
-
-// Occupancy beats per-lane interleaving here (measured, frac of the HBM roofline at N = 2 / 8 / 16 / 32 / 64 / 128):
-//   5 blocks/SM (96 regs), unroll 2:  0.57 / 0.67 / 0.59 / 0.56 / 0.46 / 0.31
-//   6 blocks/SM (80 regs), unroll 1:  0.64 / 0.71 / 0.64 / 0.61 / 0.50 / 0.33
-//   7 blocks/SM (72 regs), unroll 1:  0.67 / 0.71 / 0.66 / 0.63 / 0.52 / 0.33     <- default
-//   8 blocks/SM (64 regs, spills):    0.67 / 0.68 / 0.64 / 0.62 / 0.50 / 0.33
-#ifndef ACAS2D_TILED_MIN_BLOCKS
-#define ACAS2D_TILED_MIN_BLOCKS 7
-#endif
-#ifndef ACAS2D_TILED_UNROLL
-#define ACAS2D_TILED_UNROLL 1       /* intruders interleaved per lane (experiment switch) */
-#endif
-#define ACAS_PRAGMA(x) _Pragma(#x)
-#define ACAS_UNROLL(n) ACAS_PRAGMA(unroll n)
-template <int G, bool MINSEP>
-__global__ void __launch_bounds__(kTiledWarps * 32, ACAS2D_TILED_MIN_BLOCKS)
-step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
-                  const uint32_t magic_n)
-{
-    constexpr int E = 32 / G;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = P.n_traffic;
-    const int L = 5 + 3 * N;
-    const int TS = tiled_row_stride(N, G);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t tile_bytes = (size_t)E * TS * 16;
-    const size_t warp_bytes = tile_bytes + (((size_t)E * L * 4 + 15) & ~(size_t)15);
-    Float4 *tile = (Float4 *)(smem_raw + warp * warp_bytes);
-    float *otile = (float *)(smem_raw + warp * warp_bytes + tile_bytes);
-
-    const int64_t env0 = ((int64_t)blockIdx.x * kTiledWarps + warp) * E;     // first env of this warp
-    Tally tally;
-    tally_clear(tally);
-    if (env0 < S.B) {                                                       // warp-uniform
-        const int nvalid = (int)((S.B - env0) < (int64_t)E ? (S.B - env0) : (int64_t)E);
-        const int e = lane / G, sub = lane % G;
-        const bool valid = e < nvalid;
-        const int64_t env = env0 + (valid ? e : 0);
-        const bool lead = valid && sub == 0;
-
-        // 1. stage the traffic tile: contiguous in HBM, 16-byte cp.async, fully coalesced
-        {
-            const Float4 *src = S.thot + env0 * N;
-            const int total = nvalid * N;
-            for (int idx = lane; idx < total; idx += 32) {
-                int dst = idx;
-                if (G == 1) dst += (int)__umulhi((unsigned)idx, magic_n);        // + row (row padding)
-                __pipeline_memcpy_async(tile + dst, src + idx, 16);
-            }
-            __pipeline_commit();
-        }
-
-        // player update, redundantly in every lane of the group (game.py:222-229)
-        const Vec2d pp = S.ppos[env];
-        const PlayerAux pa = S.paux[env];
-        const bool residual = (pa.steps & kResidualBit) != 0;
-        const double dpsi = (double)actions[env] * P.dpsi_per_action;
-        Player p;
-        p.x = pp.x; p.y = pp.y;
-        player_set_heading(P, p, wrap360(pa.psi + dpsi), dpsi);
-        player_advance(P, p);
-        const int k = pa.steps & kStepsMask;
-        const int steps = k + 1;
-        float minsep = (MINSEP && lead) ? S.min_sep[env] : INFINITY;
-
-        __pipeline_wait_prior(0);
-        __syncwarp();
-
-        // 2. intruders of this lane: j = sub, sub + G, ... (rotated start for G > 1; G divides N)
-        const int per_lane = N / G;
-        const int j0 = (G == 1) ? 0 : lane % N;
-        int j = j0;
-        bool coll = false;
-        Encounter e0;
-        e0.d2 = 0.0; e0.d = 0.0f; e0.d_cpa = 0.0f; e0.v_c = 0.0f;
-        float *orow = otile + e * L;
-        const Float4 *trow = tile + e * TS;
-        const double kd = (double)k;
-        const bool any_residual = __any_sync(kFull, residual);      // injected float64 states only: keep it a branch
-ACAS_UNROLL(ACAS2D_TILED_UNROLL)
-        for (int m = 0; m < per_lane; ++m) {
-            const Float4 h = trow[j];
-            TrafficRec tr;
-            tr.x0 = (double)h.x; tr.y0 = (double)h.y; tr.psi = (double)h.z; tr.v = (double)h.w;
-            if (any_residual) {
-                if (residual) {
-                    const Residual r = S.tres[env * N + j];
-                    tr.x0 += r.x0; tr.y0 += r.y0; tr.psi += r.psi; tr.v += r.v;
-                }
-            }
-            const Intruder t = intruder_at(P, tr, kd);
-            if (MINSEP) {
-                const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
-                minsep = fminf(minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
-            }
-            const Encounter en = encounter(P, p, t);
-            if (j == 0) e0 = en;
-            coll |= en.d2 < P.coll_d2;
-            orow[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
-            orow[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
-            orow[5 + 3 * j + 2] = en.v_c * P.vc_scale;
-            j += G;
-            if (G > 1 && j >= N) j -= N;
-        }
-
-        // 3. reductions over the G lanes of the env
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            coll |= (bool)__shfl_xor_sync(kFull, (int)coll, o);
-            if (MINSEP) minsep = fminf(minsep, __shfl_xor_sync(kFull, minsep, o));
-        }
-
-        // 4. player-side observation, reward, flags (lane `sub == 0` owns intruder 0, Q7)
-        const PlayerView v = player_view(P, p, steps);
-        float r = shaped_reward(P, p, v, e0, steps);
-        const bool goal = v.dg2 < P.goal_r2;
-        const bool tout = steps > P.max_steps;
-        // game.py:279-284 (Q9): both bonuses can fall on one step; summed first so that -1000 + 1000 does not
-        // round the shaped reward to the float32 spacing at 1000
-        r += (coll ? P.reward_collision : 0.0f) + (goal ? P.reward_goal : 0.0f);
-        float ret = pa.ep_return + r;
-        const int outcome = tout ? ACAS2D_OUTCOME_TIMEOUT : coll ? ACAS2D_OUTCOME_COLLISION
-                            : goal ? ACAS2D_OUTCOME_GOAL : 0;
-        const bool done = outcome != 0;
-        int steps_out = steps | (residual ? kResidualBit : 0);
-        if (lead) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) orow[q] = v.obs[q];
-            out.reward[env] = r;
-            out.done[env] = (uint8_t)done;
-            if (out.flags) {
-                const bool oob = p.x < 0.0 || p.x > P.width || p.y < 0.0 || p.y > P.height;
-                out.flags[env] = (uint8_t)((coll ? ACAS2D_FLAG_COLLISION : 0) | (goal ? ACAS2D_FLAG_GOAL : 0) |
-                                           (tout ? ACAS2D_FLAG_TIMEOUT : 0) | (done ? ACAS2D_FLAG_DONE : 0) |
-                                           (oob ? ACAS2D_FLAG_OOB : 0));
-            }
-            if (done) {
-                if (out.outcome) out.outcome[env] = (uint8_t)outcome;
-                if (out.ep_return) out.ep_return[env] = ret;
-                if (out.ep_length) out.ep_length[env] = steps;
-                tally_add(tally, outcome, steps, ret, minsep, MINSEP);
-            }
-        }
-
-        // 5. auto-reset of the finished envs of this warp
-        const bool respawn = valid && done && P.auto_reset;
-        const unsigned respawn_mask = __ballot_sync(kFull, respawn);
-        if (respawn_mask) {
-            __syncwarp();
-            if (out.term_obs) {
-                for (int row = 0; row < nvalid; ++row) {
-                    if (!((respawn_mask >> (row * G)) & 1u)) continue;          // warp-uniform
-                    float *dst = out.term_obs + (env0 + row) * L;
-                    for (int c = lane; c < L; c += 32) dst[c] = otile[row * L + c];
-                }
-                __syncwarp();
-            }
-            if (G < 32) {
-                // A respawn is ~230 instructions per intruder; with G lanes per env a lone respawning env
-                // would run it at G/32 utilisation (1/32 in thread-per-env mode).  All 32 lanes take the intruders of each respawning
-                // env of the warp in turn instead (warp-uniform loop over the rows).
-                for (int row = 0; row < nvalid; ++row) {
-                    if (!((respawn_mask >> (row * G)) & 1u)) continue;
-                    const int64_t renv = env0 + row;
-                    uint32_t episode = 0;
-                    if (lane == 0) { episode = S.episode_idx[renv]; S.episode_idx[renv] = episode + 1u; }
-                    episode = __shfl_sync(kFull, episode, 0);
-                    const uint64_t gid = S.gid0 + (uint64_t)renv;
-                    const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
-                    Player rp;
-                    rp.x = P.player_x0; rp.y = P.player_y0;
-                    player_set_heading(P, rp, sp.player_psi, 0.0);
-                    float ms = INFINITY;
-                    float *rrow = otile + row * L;
-                    for (int jj = lane; jj < N; jj += 32) {
-                        const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, jj, sp);
-                        traffic_store(S, renv * N + jj, tr, false);
-                        const Encounter en = encounter(P, rp, intruder_at(P, tr, 0.0));
-                        ms = fminf(ms, en.d);
-                        rrow[5 + 3 * jj + 0] = en.d * P.inv_d_sep_max;
-                        rrow[5 + 3 * jj + 1] = en.d_cpa * P.inv_d_cpa_max;
-                        rrow[5 + 3 * jj + 2] = en.v_c * P.vc_scale;
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ms = fminf(ms, __shfl_xor_sync(kFull, ms, o));
-                    if (lane == 0) {
-                        const PlayerView v1 = player_view(P, rp, 1);
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) rrow[q] = v1.obs[q];
-                    }
-                    if (e == row) { p = rp; minsep = ms; steps_out = 1; ret = 0.0f; }
-                }
-            } else if (respawn) {
-                uint32_t episode = 0;
-                if (sub == 0) { episode = S.episode_idx[env]; S.episode_idx[env] = episode + 1u; }
-                episode = __shfl_sync(__activemask(), episode, e * G);
-                const uint64_t gid = S.gid0 + (uint64_t)env;
-                const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
-                p.x = P.player_x0; p.y = P.player_y0;
-                player_set_heading(P, p, sp.player_psi, 0.0);
-                minsep = INFINITY;
-                j = j0;
-                for (int m = 0; m < per_lane; ++m) {
-                    const TrafficRec tr = spawn_traffic(P, S.seed, gid, episode, j, sp);
-                    traffic_store(S, env * N + j, tr, false);
-                    const Encounter en = encounter(P, p, intruder_at(P, tr, 0.0));
-                    minsep = fminf(minsep, en.d);
-                    orow[5 + 3 * j + 0] = en.d * P.inv_d_sep_max;
-                    orow[5 + 3 * j + 1] = en.d_cpa * P.inv_d_cpa_max;
-                    orow[5 + 3 * j + 2] = en.v_c * P.vc_scale;
-                    j += G;
-                    if (G > 1 && j >= N) j -= N;
-                }
-                if (sub == 0) {
-                    const PlayerView v1 = player_view(P, p, 1);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) orow[q] = v1.obs[q];
-                }
-                steps_out = 1;
-                ret = 0.0f;
-            }
-            if (MINSEP) {      // min over the group of the spawn separations (game.py:141)
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) minsep = fminf(minsep, __shfl_xor_sync(kFull, minsep, o));
-            }
-        }
-        __syncwarp();
-
-        // 6. coalesced write-back: the rows of the warp's consecutive envs are one contiguous span of
-        //    HBM and of the (unpadded) observation tile; 128-bit stores when the span is 16-byte aligned
-        const int64_t span0 = env0 * L;
-        const int span = nvalid * L;
-        if (((span0 | span) & 3) == 0) {
-            float4 *dst4 = (float4 *)(out.obs + span0);
-            const float4 *src4 = (const float4 *)otile;
-            for (int c = lane; c < (span >> 2); c += 32) __stcs(dst4 + c, src4[c]);
-        } else {
-            float *dst = out.obs + span0;
-            for (int c = lane; c < span; c += 32) __stcs(dst + c, otile[c]);
-        }
-
-        if (lead) {
-            Vec2d np; np.x = p.x; np.y = p.y;
-            PlayerAux na; na.psi = p.psi; na.steps = steps_out; na.ep_return = ret;
-            S.ppos[env] = np;
-            S.paux[env] = na;
-            if (MINSEP) S.min_sep[env] = minsep;
-        }
-    }
-    tally_flush_warp(S.stats, tally);
-}
-
-#ifndef ACAS2D_TILED_PER_LANE
-#define ACAS2D_TILED_PER_LANE 8     /* intruders per lane the group size aims at (experiment switch).  Measured frac at
-                                       N = 8 / 16 / 32 / 64: 2 per lane 0.43 / 0.38 / 0.36 / 0.30, 4: 0.60 / 0.53 / 0.50 / 0.42,
-                                       8: 0.71 / 0.66 / 0.63 / 0.52, 16: 0.70 / 0.51 / 0.49 / 0.40 -- the player update is redone
-                                       by every lane of a group, so small groups win until a lane's loop gets too long */
-#endif
 inline int tiled_group(int N)
 {
     int want = 1;
-    while (want < 32 && want * ACAS2D_TILED_PER_LANE < N) want <<= 1;        // about eight intruders per lane
+    while (want < 32 && want * tiled_per_lane() < N) want <<= 1;
     int g = 1;
     while (g < want && N % (g * 2) == 0) g <<= 1;         // G must divide N
     return g;
 }
 
-template <int G>
-int launch_tiled(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
+// Which record the tiled kernel reads (acas2d_set_tuning's third knob / ACAS2D_TILED_KIN: -1 = by N, 0 = always the
+// 16-byte records, 1 = the kinematic cache whenever the state carries one).
+int &tiled_kin_mode()
+{
+    static int mode = [] {
+        const char *e = std::getenv("ACAS2D_TILED_KIN");
+        return e ? std::atoi(e) : -1;
+    }();
+    return mode;
+}
+
+inline bool tiled_use_kin(const StatePtrs &S, int N)
+{
+    if (!S.tkin || (N & 1)) return false;               // 24-byte rows must stay 16-byte aligned for the bulk copies
+    const int mode = tiled_kin_mode();
+    if (mode >= 0) return mode != 0;
+    return N >= 4;
+}
+
+template <int G, bool MINSEP, bool KIN>
+int launch_tiled_as(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
 {
     constexpr int E = 32 / G;
-    const size_t smem = tiled_smem_bytes(P.n_traffic, G);
+    const size_t smem = tiled_smem_bytes(P.n_traffic, G, KIN);
     const uint32_t magic_n = (uint32_t)((0x100000000ULL + (uint64_t)P.n_traffic - 1) / (uint64_t)P.n_traffic);   // idx / N for idx < 2^16
     const int64_t warps = (S.B + E - 1) / E;
     const unsigned grid = (unsigned)((warps + kTiledWarps - 1) / kTiledWarps);
-    cudaError_t err;
-    if (S.min_sep) {
-        err = cudaFuncSetAttribute(step_tiled_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        step_tiled_kernel<G, true><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out, magic_n);
-    } else {
-        err = cudaFuncSetAttribute(step_tiled_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        step_tiled_kernel<G, false><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out, magic_n);
-    }
+    cudaError_t err = cudaFuncSetAttribute(step_tiled_kernel<G, MINSEP, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    if (G > 1 && S.pstage)                      // the float64 player update, once per env, as its own launch
+        player_phase_kernel<<<(unsigned)((S.B + 127) / 128), 128, 0, st>>>(P, S, actions);
+    step_tiled_kernel<G, MINSEP, KIN><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out, magic_n);
     return 0;
+}
+
+template <int G>
+int launch_tiled(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
+{
+    const bool kin = tiled_use_kin(S, P.n_traffic);
+    if (S.min_sep) return kin ? launch_tiled_as<G, true, true>(P, S, actions, out, st) : launch_tiled_as<G, true, false>(P, S, actions, out, st);
+    return kin ? launch_tiled_as<G, false, true>(P, S, actions, out, st) : launch_tiled_as<G, false, false>(P, S, actions, out, st);
 }
 
 // ---------------------------------------------------------------- reset / inject / extract
@@ -905,6 +656,9 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
         sub.tres = (char *)state->tres + 32 * N * off;
         sub.episode_idx = state->episode_idx + off;
         sub.min_sep = state->min_sep ? state->min_sep + off : nullptr;
+        sub.tkin = state->tkin ? (char *)state->tkin + 24 * N * off : nullptr;
+        sub.tpsi0 = state->tpsi0 ? state->tpsi0 + off : nullptr;
+        sub.pstage = state->pstage ? (char *)state->pstage + ACAS2D_PSTAGE_BYTES * off : nullptr;   // [7][n] block of this chunk
         sub.env_id_offset = state->env_id_offset + (uint64_t)off;
         acas2d_step_aux sa = {};
         if (aux) {
@@ -1228,6 +982,13 @@ int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop)
 {
     if (n1_occupancy >= 1 && n1_occupancy <= 4) tuning().n1_occupancy = n1_occupancy;
     if (force_loop >= 0) tuning().force_loop = force_loop != 0;
+    return 0;
+}
+
+int acas2d_set_tiled_tuning(int32_t kin_mode, int32_t per_lane)
+{
+    if (kin_mode >= -1 && kin_mode <= 1) tiled_kin_mode() = kin_mode;
+    if (per_lane >= 1 && per_lane <= 64) tiled_per_lane() = per_lane;
     return 0;
 }
 

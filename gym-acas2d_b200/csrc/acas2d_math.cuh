@@ -69,7 +69,8 @@ struct DevParams {
     float reward_goal, reward_collision;
     float tn_x_span_f, tn_y_span_f, factor_min_f, factor_span_f, airspeed_f;   // float32 spawn of intruders n>0
     // ---- integers
-    int32_t n_traffic, max_steps, auto_reset, pad_;
+    int32_t n_traffic, max_steps, auto_reset;
+    int32_t q3_trivial;     // every spawned intruder flies at exactly AIRSPEED (factor min == max == 1): Q3's term == dy
 };
 
 // forward: used by sincos_deg below
@@ -158,6 +159,43 @@ ACAS_HD int acas_rint_i(double x)
 #endif
 }
 
+// Conversions that touch float64 (F2F, F2I, I2F with a 64-bit side) and MUFU share one 16-lane/clk/SM pipe on
+// sm_100 (measured, tools/ubench_pipes.cu: DFMA 64, F2F.F64.F32 / I2F.F64 / F2I.F64 / MUFU 16 thread-ops/clk/SM):
+// a warp-wide conversion occupies it for 8 cycles -- as long as four DFMAs.  The per-intruder loops are bound by
+// that pipe, so the conversions that can be done exactly (or within one float32 ulp) on the integer / FP64
+// pipes are done there.
+
+// rint(x) as a double plus the integer in the low word, |x| < 2^51: one DADD instead of F2I.F64 + I2F.F64.
+ACAS_HD double acas_rint_magic(double x, int *q)
+{
+#if defined(__CUDA_ARCH__)
+    const double t = x + 6755399441055744.0;            // 2^52 + 2^51: the integer lands in the low mantissa bits
+    *q = __double2loint(t);
+    return t - 6755399441055744.0;
+#else
+    const double r = nearbyint(x);
+    *q = (int)r;
+    return r;
+#endif
+}
+
+// float32 value of a NON-NEGATIVE double, truncated (result <= v, within one float32 ulp); values below
+// 2^-126 give 0..7 denormal ulps (flushed by the .ftz consumers), v must be < 2^128.  Three integer
+// instructions instead of one F2F.F32.F64.  Only for quantities that feed sqrt / rsqrt of an output.
+#ifndef ACAS2D_ALU_D2F
+#define ACAS2D_ALU_D2F 1
+#endif
+ACAS_HD float acas_d2f_pos(double v)
+{
+#if defined(__CUDA_ARCH__) && ACAS2D_ALU_D2F
+    const int hi = __double2hiint(v) - 0x38000000;      // re-bias the exponent: 1023 -> 127
+    const unsigned lo = (unsigned)__double2loint(v);
+    return __uint_as_float(__funnelshift_l(lo, (unsigned)max(hi, 0), 3));
+#else
+    return (float)v;
+#endif
+}
+
 // sin and cos of an angle given in DEGREES (the unit the reference keeps headings in,
 // aircraft.py:22-23).  The argument is reduced in degrees, where the reduction psi - 90*q is
 // exact, then one multiply by pi/180 lands in [-pi/4, pi/4] for the fdlibm kernel polynomials.
@@ -168,8 +206,9 @@ ACAS_HD void sincos_deg(double deg, double *s, double *c)
 {
     // (the coefficients stay 64-bit immediates: moved to the constant bank, ptxas copies them into vector
     //  registers every iteration -- as many instructions, plus a spill in the tiled kernel)
-    const int q = acas_rint_i(deg * (1.0 / 90.0));
-    const double r = fma((double)q, -90.0, deg);            // exact
+    int q;
+    const double qd = acas_rint_magic(deg * (1.0 / 90.0), &q);
+    const double r = fma(qd, -90.0, deg);                   // exact
     const double t = r * kDeg2Rad;
     const double z = t * t;
     double ps = 1.58969099521155010221e-10;
@@ -307,10 +346,15 @@ ACAS_HD Encounter encounter(const DevParams &P, const Player &p, const Intruder 
     const double q2 = qx * qx + qy * qy;
     const double dot = ex * qx + ey * qy;
 
-    e.d = acas_sqrtf((float)e.d2);
-    const float cr = (float)cross * acas_rsqrtf((float)w2);
+    e.d = acas_sqrtf(acas_d2f_pos(e.d2));
+    const float cr = (float)cross * acas_rsqrtf(acas_d2f_pos(w2));
+#if defined(__CUDA_ARCH__)
+    // sign(wx) * cr on the integer pipe (wx is a float64 difference: an exact zero is +0, so "wx < 0" is its sign bit)
+    e.d_cpa = __int_as_float(__float_as_int(cr) ^ (__double2hiint(wx) & (int)0x80000000));
+#else
     e.d_cpa = (wx < 0.0) ? -cr : cr;
-    e.v_c = (float)dot * acas_rsqrtf((float)q2);          // displacement units; * FPS = px/s (Q4)
+#endif
+    e.v_c = (float)dot * acas_rsqrtf(acas_d2f_pos(q2));   // displacement units; * FPS = px/s (Q4)
     return e;
 }
 

@@ -16,24 +16,27 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 CSRC_DIR = os.path.join(_PKG_ROOT, "csrc")
 REPO_ROOT = os.path.dirname(_PKG_ROOT)
 LIB_PATH = os.environ.get("ACAS2D_LIB") or os.path.join(CSRC_DIR, "libacas2d_b200.so")   # ACAS2D_LIB: experiment builds
-SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh", "acas2d_policy_tc.cuh", "acas2d_dev.cuh", "acas2d_ppo.cuh")
+SOURCES = ("acas2d_kernels.cu", "acas2d_env.cuh", "acas2d_math.cuh", "acas2d_policy.cuh", "acas2d_policy_tc.cuh", "acas2d_dev.cuh", "acas2d_ppo.cuh",
+           "acas2d_tiled.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_TRAFFIC = 1024
 STAT_SLOTS, STAT_FIELDS = 128, 16
 STAT_NAMES = ("episodes", "goal", "collision", "timeout", "length_sum", "return_fx", "min_sep_fx")
 STAT_FX_SCALE = 1048576.0
 FLAG_COLLISION, FLAG_GOAL, FLAG_TIMEOUT, FLAG_DONE, FLAG_OOB = 1, 2, 4, 8, 16
 STEPS_RESIDUAL_BIT = 0x40000000
+STEPS_COMPACT_BIT, STEPS_DOWN_BIT, STEPS_MASK = 0x20000000, 0x10000000, 0x0FFFFFFF
 POLICY_FLOATS = 4804
 PPO_PARAM_FLOATS = 2 * POLICY_FLOATS + 4
 PPO_LOG_STD = 2 * POLICY_FLOATS
 PPO_PARTIAL_FLOATS, PPO_MAX_CTAS = 4816, 148
 PPO_WORKSPACE_FLOATS = 64 + 2 * PPO_MAX_CTAS * PPO_PARTIAL_FLOATS
 PPO_MAX_RANKS = 16
+PSTAGE_BYTES = 112
 PPO_EXCHANGE_FLOATS = 2 * PPO_PARAM_FLOATS + PPO_MAX_RANKS
 PPO_LOSS_STATS = 8
 
@@ -41,7 +44,7 @@ EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
            "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render",
            "acas2d_ppo_values", "acas2d_ppo_gae", "acas2d_ppo_grad", "acas2d_ppo_adam", "acas2d_ppo_step",
-           "acas2d_ppo_prepare", "acas2d_policy_step_dyn", "acas2d_step_k")
+           "acas2d_ppo_prepare", "acas2d_policy_step_dyn", "acas2d_step_k", "acas2d_set_tiled_tuning")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -64,7 +67,8 @@ class State(ctypes.Structure):
                 ("thot", ctypes.c_void_p), ("tres", ctypes.c_void_p),
                 ("episode_idx", ctypes.c_void_p), ("min_sep", ctypes.c_void_p),
                 ("stats", ctypes.c_void_p),
-                ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_uint64)]
+                ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_uint64),
+                ("tkin", ctypes.c_void_p), ("tpsi0", ctypes.c_void_p), ("pstage", ctypes.c_void_p)]
 
 
 class PpoConfig(ctypes.Structure):
@@ -120,6 +124,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_launch_count.restype = ctypes.c_int64
     lib.acas2d_set_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.acas2d_set_n1_kernel.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    lib.acas2d_set_tiled_tuning.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.acas2d_policy_step.argtypes = [PP, SP, vp, ctypes.c_float, vp, vp, vp, vp, vp, vp, AP, ctypes.c_int32,
                                        ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, vp]
     lib.acas2d_policy_step_dyn.argtypes = [PP, SP, vp, ctypes.c_float, vp, vp, vp, vp, vp, vp, AP, ctypes.c_int32,

@@ -70,6 +70,11 @@ class BatchedACAS2D:
             self.paux = torch.zeros(B, 2, dtype=f64, device=dev)          # 16 B records {psi, steps, ep_return}
             self.thot = torch.zeros(B, N, 4, dtype=f32, device=dev)          # {x0, y0, psi, v}: all a step reads
             self.tres = torch.zeros(B, N, 4, dtype=f64, device=dev)          # cold float64 remainders (injected states)
+            # kinematic cache (N > 1): 24 B / intruder {x0, y0 float32; dx, dy float64}, written at spawn / injection
+            self.tkin = torch.zeros(B, N, 3, dtype=f64, device=dev) if N > 1 else None
+            self.tpsi0 = None
+            # per-step scratch of the player pre-pass (N > 1): 7 x 16 B per env, structure of arrays
+            self.pstage = torch.zeros(_native.PSTAGE_BYTES // 16, B, 4, dtype=f32, device=dev) if N > 1 else None
             self.episode_idx = torch.zeros(B, dtype=torch.int32, device=dev)
             self.min_sep = torch.zeros(B, dtype=f32, device=dev) if track_min_sep else None
             self.stats = torch.zeros(_native.STAT_SLOTS, _native.STAT_FIELDS, dtype=torch.int64, device=dev)
@@ -86,7 +91,10 @@ class BatchedACAS2D:
             num_envs=B, ppos=self.ppos.data_ptr(), paux=self.paux.data_ptr(), thot=self.thot.data_ptr(),
             tres=self.tres.data_ptr(), episode_idx=self.episode_idx.data_ptr(),
             min_sep=self.min_sep.data_ptr() if track_min_sep else None,
-            stats=self.stats.data_ptr(), seed=self.seed, env_id_offset=self.env_id_offset)
+            stats=self.stats.data_ptr(), seed=self.seed, env_id_offset=self.env_id_offset,
+            tkin=self.tkin.data_ptr() if self.tkin is not None else None,
+            tpsi0=self.tpsi0.data_ptr() if self.tpsi0 is not None else None,
+            pstage=self.pstage.data_ptr() if self.pstage is not None else None)
         self._aux_full = StepAux(flags=self.flags.data_ptr(), outcome=self.outcome.data_ptr(),
                                  term_obs=self.term_obs.data_ptr(), ep_return=self.ep_return.data_ptr(),
                                  ep_length=self.ep_length.data_ptr())

@@ -34,6 +34,16 @@
  *   tres        double[B][N][4] full - float32(full) of the same four values.  Cold: written by
  *                               acas2d_inject_state, read by step / extract only for envs whose
  *                               paux.steps carries ACAS2D_STEPS_RESIDUAL_BIT (injected float64 states).
+ *   tkin        24 B / intruder { float x0, y0; double dx, dy }  OPTIONAL kinematic cache (N > 1): the intruder's
+ *                               displacement per step v*dt*(cos psi, sin psi) in float64, written once at spawn /
+ *                               injection next to thot.  With it the step reads 24 B per intruder and evaluates no
+ *                               sin / cos per intruder per step (a heading never changes, game.py:243-245); without
+ *                               it (NULL) the step derives the same values from thot every step.  Same results.
+ *   tpsi0       float[B]        OPTIONAL compact form of intruder 0 for N == 1: the reference spawns intruder 0 at
+ *                               x = WIDTH - COLLISION_RADIUS, y in {CR, HEIGHT - CR} with speed AIRSPEED * factor
+ *                               (game.py:97-106), so a spawned (not injected) env is described by its heading and
+ *                               one bit.  Envs whose paux.steps carries ACAS2D_STEPS_COMPACT_BIT (+ ACAS2D_STEPS_DOWN_BIT)
+ *                               are stepped from these 4 bytes instead of the 16-byte thot record (which stays valid).
  *   episode_idx uint32[B]       episodes started by this env (Philox counter word 2)
  *   min_sep     float[B]        running minimum separation of the episode, or NULL
  *   stats       int64[ACAS2D_STAT_SLOTS][ACAS2D_STAT_FIELDS]  finished-episode counters
@@ -47,7 +57,7 @@
 extern "C" {
 #endif
 
-#define ACAS2D_ABI_VERSION 1
+#define ACAS2D_ABI_VERSION 2
 
 #define ACAS2D_E_NULL        (-1)  /* required pointer is NULL */
 #define ACAS2D_E_BAD_TRAFFIC (-2)  /* n_traffic < 1 (reference precondition, game.py:146-147) or > ACAS2D_MAX_TRAFFIC */
@@ -55,9 +65,15 @@ extern "C" {
 #define ACAS2D_E_NO_DEVICE   (-4)  /* no CUDA device / not an sm_100 device */
 
 #define ACAS2D_MAX_TRAFFIC 1024
+#define ACAS2D_PSTAGE_BYTES 112
 
 /* bit of paux.steps: this env's intruder records need their float64 residuals (tres) */
 #define ACAS2D_STEPS_RESIDUAL_BIT 0x40000000
+/* bits of paux.steps (N == 1, state->tpsi0 given): intruder 0 is in its spawn pattern, heading in tpsi0[env];
+ * DOWN = it started at the bottom edge (starts_down, game.py:98-101) */
+#define ACAS2D_STEPS_COMPACT_BIT  0x20000000
+#define ACAS2D_STEPS_DOWN_BIT     0x10000000
+#define ACAS2D_STEPS_MASK         0x0fffffff
 
 /* step flags (uint8 per env) */
 #define ACAS2D_FLAG_COLLISION 1u   /* game.py:185-189  d < 2*COLLISION_RADIUS for any intruder */
@@ -121,6 +137,11 @@ typedef struct acas2d_state {
     int64_t  *stats;          /* optional */
     uint64_t  seed;           /* Philox key */
     uint64_t  env_id_offset;  /* global id of env 0 (rank sharding: spawns do not depend on the GPU count) */
+    void     *tkin;           /* optional (N > 1): 24 B / intruder kinematic cache, see above */
+    float    *tpsi0;          /* optional (N == 1): compact intruder-0 headings, see above */
+    void     *pstage;         /* optional scratch (N > 1), ACAS2D_PSTAGE_BYTES per env: with it the float64 player update of
+                                 a step runs as its own one-thread-per-env launch and the tiled kernel's lanes read its
+                                 result, instead of every lane of an env's group redoing it; contents are per-step */
 } acas2d_state;
 
 /* Optional per-step outputs (any pointer may be NULL). */
@@ -324,6 +345,11 @@ int acas2d_set_tuning(int32_t n1_occupancy, int32_t force_loop);
  * persistent kernel fed by a TMA bulk-copy ring of `stages` (2..5) input tiles (default), 0 = the
  * direct one-thread-per-env kernel, negative = unchanged.  Both are bit-identical in results. */
 int acas2d_set_n1_kernel(int32_t use_tma, int32_t stages);
+
+/* N_TRAFFIC > 1 kernel tuning (process-wide; env ACAS2D_TILED_KIN / ACAS2D_TILED_PER_LANE): kin_mode 1 = read the
+ * kinematic cache (state->tkin) whenever it is there, 0 = always the 16-byte records, -1 = choose by N (default);
+ * per_lane = intruders per lane the lanes-per-env choice aims at (default 8), 0 = unchanged.  Results do not change. */
+int acas2d_set_tiled_tuning(int32_t kin_mode, int32_t per_lane);
 
 #ifdef __cplusplus
 }
