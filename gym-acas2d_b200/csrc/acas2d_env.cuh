@@ -263,13 +263,32 @@ ACAS_HD TrafficRec spawn_traffic(const DevParams &P, uint64_t seed, uint64_t gid
 // ---------------------------------------------------------------- N_TRAFFIC == 1
 struct Env1 {
     double px, py, psi;
-    int32_t steps;          // game.steps, without the residual bit
-    bool residual;
+    int32_t steps;          // game.steps, without the flag bits
+    int32_t bits;           // the flag bits of paux.steps (kResidualBit | kCompactBit | kDownBit)
     float ret;
     TrafficRec tr;
     float minsep;
     bool respawned;
 };
+
+// N == 1, compact form (acas2d_b200.h "tpsi0"): intruder 0 of a SPAWNED env sits in the reference's spawn pattern
+// (game.py:97-106) -- fixed x, one of two y, fixed speed when the speed factor is a constant -- so its heading
+// and one bit describe it.  The record a spawn writes is rounded to float32 (spawn_traffic); these are the same
+// roundings.
+ACAS_HD bool compact_ok(const DevParams &P, const StatePtrs &S)
+{
+    return S.tpsi0 != nullptr && P.factor_span == 0.0 && P.n_traffic == 1;
+}
+
+ACAS_HD TrafficRec compact_traffic(const DevParams &P, float psi, bool down)
+{
+    TrafficRec t;
+    t.x0 = (double)(float)P.t0_x;
+    t.y0 = (double)(float)(P.t0_y_up + (down ? 1.0 : 0.0) * P.t0_y_span);
+    t.v = (double)(float)((P.factor_min + P.factor_span * 0.5) * P.airspeed);      // factor_span == 0 here
+    t.psi = (double)psi;
+    return t;
+}
 
 ACAS_HD void store_obs8(float *row, const PlayerView &v, const Encounter &e, const DevParams &P)
 {
@@ -285,10 +304,39 @@ ACAS_HD void store_obs8(float *row, const PlayerView &v, const Encounter &e, con
 #endif
 }
 
+// New game for a single-intruder env (SB3 DummyVecEnv semantics): Philox spawn, reset
+// observation (environment.py:47: steps becomes 1), intruder records.  The caller stores the player state.
+template <bool EMIT>
+ACAS_HD void respawn_env1(const DevParams &P, const StatePtrs &S, Env1 &e, int64_t i, const Sinks &out)
+{
+    const uint32_t episode = S.episode_idx[i];
+    S.episode_idx[i] = episode + 1u;
+    const uint64_t gid = S.gid0 + (uint64_t)i;
+    const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
+    Player p;
+    p.x = P.player_x0; p.y = P.player_y0;
+    player_set_heading(P, p, sp.player_psi, 0.0);                          // a_lat = 0 in a new game
+    e.tr = spawn_traffic(P, S.seed, gid, episode, 0, sp);
+    const Intruder t = intruder_at(P, e.tr, 0.0);
+    const PlayerView v1 = player_view(P, p, 1);
+    const Encounter e1 = encounter(P, p, t);
+    if (EMIT) store_obs8(out.obs + 8 * i, v1, e1, P);
+    e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = 1; e.ret = 0.0f;
+    e.bits = 0;
+    if (compact_ok(P, S)) {
+        S.tpsi0[i] = (float)e.tr.psi;
+        e.bits = kCompactBit | (sp.y != P.t0_y_up ? kDownBit : 0);
+    }
+    e.minsep = e1.d;                                                       // game.py:141
+    e.respawned = true;
+}
+
 // One environment step for a single-intruder env held in registers.
-// EMIT = write per-step outputs through `out`; i = local env index.
-template <bool MINSEP, bool EMIT>
-ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float action,
+// EMIT = write per-step outputs through `out`; i = local env index.  DEFER: a finished env that must respawn is
+// left untouched (its terminal outputs are written) and `true` is returned -- the caller respawns it later with
+// respawn_env1 (the persistent kernel queues these so that a lone respawning lane does not hold up its warp).
+template <bool MINSEP, bool EMIT, bool DEFER = false>
+ACAS_HD bool step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float action,
                        int64_t i, const Sinks &out, Tally &tally, float *reward_acc)
 {
     // ---- game.action (game.py:222-247)
@@ -299,7 +347,7 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
     player_advance(P, p);
 
     const int k = e.steps;                                                 // intruder moves after this step
-    Intruder t = intruder_at(P, e.tr, (double)k);                          // game.py:243-245
+    const Intruder t = intruder_at(P, e.tr, (double)k);                    // game.py:243-245
     if (MINSEP) {                                                          // game.py:237 (Q10: old traffic)
         const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;
         e.minsep = fminf(e.minsep, acas_sqrtf((float)(ox * ox + oy * oy)));
@@ -345,10 +393,10 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
             tally_add(tally, outcome, steps, ret, e.minsep, MINSEP);
         }
         e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = steps; e.ret = ret;
-        return;
+        return false;
     }
 
-    // ---- auto-reset (SB3 DummyVecEnv semantics)
+    // ---- auto-reset: terminal outputs now, the new game now or (DEFER) later
     if (EMIT) {
         if (out.term_obs) store_obs8(out.term_obs + 8 * i, v, en, P);
         if (out.outcome) out.outcome[i] = (uint8_t)outcome;
@@ -356,22 +404,9 @@ ACAS_HD void step_env1(const DevParams &P, const StatePtrs &S, Env1 &e, float ac
         if (out.ep_length) out.ep_length[i] = steps;
     }
     tally_add(tally, outcome, steps, ret, e.minsep, MINSEP);
-
-    const uint32_t episode = S.episode_idx[i];
-    S.episode_idx[i] = episode + 1u;
-    const uint64_t gid = S.gid0 + (uint64_t)i;
-    const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
-    p.x = P.player_x0; p.y = P.player_y0;
-    player_set_heading(P, p, sp.player_psi, 0.0);                          // a_lat = 0 in a new game
-    e.tr = spawn_traffic(P, S.seed, gid, episode, 0, sp);
-    t = intruder_at(P, e.tr, 0.0);
-    const PlayerView v1 = player_view(P, p, 1);                            // environment.py:47: steps becomes 1
-    const Encounter e1 = encounter(P, p, t);
-    if (EMIT) store_obs8(out.obs + 8 * i, v1, e1, P);
-    e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = 1; e.ret = 0.0f;
-    e.residual = false;
-    e.minsep = e1.d;                                                       // game.py:141
-    e.respawned = true;
+    if (DEFER) return true;
+    respawn_env1<EMIT>(P, S, e, i, out);
+    return false;
 }
 
 ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
@@ -380,8 +415,8 @@ ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
     const PlayerAux pa = S.paux[i];
     e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.ret = pa.ep_return;
     e.steps = pa.steps & kStepsMask;
-    e.residual = (pa.steps & kResidualBit) != 0;
-    e.tr = traffic_load(S, i, e.residual);
+    e.bits = pa.steps & ~kStepsMask;
+    e.tr = traffic_load(S, i, (e.bits & kResidualBit) != 0);          // the 16-byte record is valid in compact form too
     e.minsep = minsep ? S.min_sep[i] : 0.0f;
     e.respawned = false;
 }
@@ -389,7 +424,7 @@ ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
 ACAS_HD void store_env1(const StatePtrs &S, int64_t i, const Env1 &e, bool minsep)
 {
     Vec2d pp; pp.x = e.px; pp.y = e.py;
-    PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps | (e.residual ? kResidualBit : 0); pa.ep_return = e.ret;
+    PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps | e.bits; pa.ep_return = e.ret;
     {
         Float4 a, b;                                   // two 16-byte records, stored as 128-bit words
         memcpy(&a, &pp, 16); memcpy(&b, &pa, 16);
@@ -533,6 +568,10 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     }
     Vec2d np; np.x = p.x; np.y = p.y;
     PlayerAux na; na.psi = p.psi; na.steps = 1 | spawn_bits(P, S); na.ep_return = 0.0f;
+    if (compact_ok(P, S)) {                                               // N == 1: the compact form of intruder 0
+        S.tpsi0[i] = (float)sp.psi;
+        na.steps |= kCompactBit | (sp.y != P.t0_y_up ? kDownBit : 0);
+    }
     S.ppos[i] = np;
     S.paux[i] = na;
     if (S.min_sep) S.min_sep[i] = minsep;

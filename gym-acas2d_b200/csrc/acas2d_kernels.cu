@@ -109,20 +109,33 @@ step_n1_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ a
 // streams that still keeps the schedulers fed (2 CTAs/SM x 2 stages).
 // TILE = envs per tile = threads per CTA (256 or 512); a stage holds ppos | paux | thot | action.
 
-template <int STAGES, int OCC, int TILE>
+// COMPACT (state->tpsi0 given): the intruder part of a stage is the 4-byte heading array instead of the 16-byte
+// records -- 40 instead of 52 bytes read per env-step; envs that are not in the spawn pattern (injected states)
+// fetch their record with a plain load.
+// Respawns are DEFERRED: a finished env leaves its index in a shared-memory queue and the CTA respawns all of
+// them together after its last tile.  A respawn is ~600 instructions on one lane; done in line it holds up
+// its warp and, through the per-tile barrier that recycles the stage, the whole CTA -- with ~0.1 % of the
+// envs finishing per step, one tile in five has one (measured: 92.6 us per step in steady state against
+// 82.4 us with no episode ending).
+constexpr int kRespawnQueue = 256;
+
+template <int STAGES, int OCC, int TILE, bool COMPACT>
 __global__ void __launch_bounds__(TILE, OCC)
 step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
                    const long long full_tiles)
 {
-    constexpr int kTileEnvs = TILE, kStageBytes = TILE * (16 + 16 + 16 + 4);
-    constexpr int kOffPaux = TILE * 16, kOffThot = TILE * 32, kOffAct = TILE * 48;
+    constexpr int kTileEnvs = TILE, kTraffic = COMPACT ? 4 : 16, kStageBytes = TILE * (16 + 16 + kTraffic + 4);
+    constexpr int kOffPaux = TILE * 16, kOffThot = TILE * 32, kOffAct = TILE * (32 + kTraffic);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+    __shared__ long long queue[kRespawnQueue];
+    __shared__ int queue_count;
     const int tid = threadIdx.x;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        queue_count = 0;
     }
     __syncthreads();
 
@@ -143,7 +156,8 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         mbar_expect_tx(bar, kStageBytes);
         tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, bar, pol);
         tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, bar, pol);
-        tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar, pol);
+        if (COMPACT) tma_load_1d(base + kOffThot, S.tpsi0 + e0, kTileEnvs * 4, bar, pol);
+        else tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar, pol);
         tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, bar, pol);
     };
 
@@ -157,6 +171,16 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
 
     Tally tally;
     tally_clear(tally);
+    auto finish = [&](Env1 &e, float a, int64_t i) {
+        e.minsep = 0.0f;
+        e.respawned = false;
+        if (step_env1<false, true, true>(P, S, e, a, i, out, tally, nullptr)) {
+            const int slot = atomicAdd(&queue_count, 1);
+            if (slot < kRespawnQueue) { queue[slot] = i; return; }
+            respawn_env1<true>(P, S, e, i, out);           // queue full (a whole tile finishing at once): in line
+        }
+        store_env1(S, i, e, false);
+    };
     int it = 0;
     for (long long tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
         const int s = it % STAGES;
@@ -164,7 +188,10 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         const unsigned char *base = smem + s * kStageBytes;
         const Vec2d pp = ((const Vec2d *)base)[tid];
         const PlayerAux pa = ((const PlayerAux *)(base + kOffPaux))[tid];
-        const Float4 h = ((const Float4 *)(base + kOffThot))[tid];
+        Float4 h;
+        float tpsi = 0.0f;
+        if (COMPACT) tpsi = ((const float *)(base + kOffThot))[tid];
+        else h = ((const Float4 *)(base + kOffThot))[tid];
         const float a = ((const float *)(base + kOffAct))[tid];
         // WAR across proxies: the generic-proxy shared loads above must have been performed before
         // the async proxy (the TMA refill issued below) may overwrite the stage.  bar.sync alone does
@@ -180,18 +207,22 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         Env1 e;
         e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.ret = pa.ep_return;
         e.steps = pa.steps & kStepsMask;
-        e.residual = (pa.steps & kResidualBit) != 0;
-        e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
-        if (__any_sync(kFull, e.residual)) {               // injected float64 states only: a real (warp-uniform) branch
-            if (e.residual) {
-                const Residual r = S.tres[i];
-                e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
+        e.bits = pa.steps & ~kStepsMask;
+        if (COMPACT) {
+            e.tr = compact_traffic(P, tpsi, (e.bits & kDownBit) != 0);
+            if (__any_sync(kFull, (e.bits & kCompactBit) == 0)) {      // injected states only: a real (warp-uniform) branch
+                if ((e.bits & kCompactBit) == 0) e.tr = traffic_load(S, i, (e.bits & kResidualBit) != 0);
+            }
+        } else {
+            e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
+            if (__any_sync(kFull, (e.bits & kResidualBit) != 0)) {     // injected float64 states only
+                if (e.bits & kResidualBit) {
+                    const Residual r = S.tres[i];
+                    e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
+                }
             }
         }
-        e.minsep = 0.0f;
-        e.respawned = false;
-        step_env1<false, true>(P, S, e, a, i, out, tally, nullptr);
-        store_env1(S, i, e, false);
+        finish(e, a, i);
     }
 
     // ragged tail (B % 256 envs): one CTA, plain loads
@@ -201,9 +232,19 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         if (i < S.B) {
             Env1 e;
             load_env1(S, i, e, false);
-            step_env1<false, true>(P, S, e, __ldcs(actions + i), i, out, tally, nullptr);
-            store_env1(S, i, e, false);
+            finish(e, __ldcs(actions + i), i);
         }
+    }
+
+    // the deferred respawns of this CTA, one lane each
+    __syncthreads();
+    const int queued = queue_count < kRespawnQueue ? queue_count : kRespawnQueue;
+    for (int q = tid; q < queued; q += TILE) {
+        const int64_t i = queue[q];
+        Env1 e;
+        e.minsep = 0.0f;
+        respawn_env1<true>(P, S, e, i, out);
+        store_env1(S, i, e, false);
     }
     tally_flush_warp(S.stats, tally);
 }
@@ -211,22 +252,29 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
 template <int STAGES, int OCC, int TILE = 256>
 int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
 {
-    constexpr int kTileEnvs = TILE, kStageBytes = TILE * (16 + 16 + 16 + 4);
+    constexpr int kTileEnvs = TILE;
+    const bool compact = compact_ok(P, S) && (((uintptr_t)S.tpsi0) & 15) == 0;
+    const int stage_bytes = TILE * (16 + 16 + (compact ? 4 : 16) + 4);
     static int sms = 0;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (!attr_set[dev & 63]) {                      // function attributes are per device
-        cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             STAGES * kStageBytes + 64);
+        cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC, TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             STAGES * TILE * 52 + 64);
+        cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC, TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             STAGES * TILE * 40 + 64);
         attr_set[dev & 63] = true;
     }
     const long long full_tiles = S.B / kTileEnvs;
     long long grid = (long long)sms * OCC;
     const long long tiles = full_tiles + ((S.B % kTileEnvs) ? 1 : 0);
     if (grid > tiles) grid = tiles;
-    step_n1_tma_kernel<STAGES, OCC, TILE><<<(unsigned)grid, TILE, STAGES * kStageBytes + 64, st>>>(P, S, actions, out, full_tiles);
+    if (compact)
+        step_n1_tma_kernel<STAGES, OCC, TILE, true><<<(unsigned)grid, TILE, STAGES * stage_bytes + 64, st>>>(P, S, actions, out, full_tiles);
+    else
+        step_n1_tma_kernel<STAGES, OCC, TILE, false><<<(unsigned)grid, TILE, STAGES * stage_bytes + 64, st>>>(P, S, actions, out, full_tiles);
     return 0;
 }
 
@@ -371,7 +419,10 @@ inline bool tiled_use_kin(const StatePtrs &S, int N)
     if (!S.tkin || (N & 1)) return false;               // 24-byte rows must stay 16-byte aligned for the bulk copies
     const int mode = tiled_kin_mode();
     if (mode >= 0) return mode != 0;
-    return N >= 4;
+    // measured (B200, fraction of the HBM roofline, cache vs records): N = 64 at 262 144 envs 0.61 vs 0.53, N = 256 at
+    // 65 536 envs 0.35 vs 0.30, N = 8 at 65 536 envs 0.38 vs 0.33 -- but N = 8 at 1 Mi envs 0.67 vs 0.71: with few
+    // intruders per env the step is HBM-bound once the cache no longer fits L2, and the cache is 8 bytes more per intruder
+    return N >= 16 || (double)S.B * N * 24.0 <= 48e6;
 }
 
 template <int G, bool MINSEP, bool KIN>
@@ -681,6 +732,23 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
         ACAS_TRY(cudaStreamWaitEvent(st, pipe->done[i], 0));
     }
 #undef ACAS_TRY
+    return (int)cudaStreamSynchronize(st);
+}
+
+int acas2d_step_host_packed(const acas2d_params *params, const acas2d_state *state, const float *h_actions,
+                            float *d_actions, float *obs, float *reward, uint8_t *done, const acas2d_step_aux *aux,
+                            const void *d_packed, void *h_packed, int64_t packed_bytes, void *stream)
+{
+    if (int e = check_args(params, state)) return e;
+    if (state->num_envs == 0) return 0;
+    if (!h_actions || !d_actions || !obs || !reward || !done || !d_packed || !h_packed) return ACAS2D_E_NULL;
+    if (packed_bytes <= 0) return ACAS2D_E_BAD_SIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, sizeof(float) * state->num_envs, cudaMemcpyHostToDevice, st);
+    if (err != cudaSuccess) return (int)err;
+    if (int e = acas2d_step(params, state, d_actions, obs, reward, done, aux, stream)) return e;
+    err = cudaMemcpyAsync(h_packed, d_packed, (size_t)packed_bytes, cudaMemcpyDeviceToHost, st);
+    if (err != cudaSuccess) return (int)err;
     return (int)cudaStreamSynchronize(st);
 }
 

@@ -260,9 +260,9 @@ policy_step_n1_tc_kernel(const DevParams P, const StatePtrs S, const float *__re
             Env1 e;
             e.px = pp.x; e.py = pp.y; e.psi = pa.psi; e.ret = pa.ep_return;
             e.steps = pa.steps & kStepsMask;
-            e.residual = (pa.steps & kResidualBit) != 0;
+            e.bits = pa.steps & ~kStepsMask;
             e.tr.x0 = (double)h.x; e.tr.y0 = (double)h.y; e.tr.psi = (double)h.z; e.tr.v = (double)h.w;
-            if (__builtin_expect(e.residual, 0)) {
+            if (__builtin_expect((e.bits & kResidualBit) != 0, 0)) {
                 const Residual r = S.tres[i];
                 e.tr.x0 += r.x0; e.tr.y0 += r.y0; e.tr.psi += r.psi; e.tr.v += r.v;
             }

@@ -72,21 +72,18 @@ class BatchedACAS2D:
             self.tres = torch.zeros(B, N, 4, dtype=f64, device=dev)          # cold float64 remainders (injected states)
             # kinematic cache (N > 1): 24 B / intruder {x0, y0 float32; dx, dy float64}, written at spawn / injection
             self.tkin = torch.zeros(B, N, 3, dtype=f64, device=dev) if N > 1 else None
-            self.tpsi0 = None
+            self.tpsi0 = torch.zeros(B, dtype=f32, device=dev) if N == 1 else None     # compact intruder-0 headings
             # per-step scratch of the player pre-pass (N > 1): 7 x 16 B per env, structure of arrays
             self.pstage = torch.zeros(_native.PSTAGE_BYTES // 16, B, 4, dtype=f32, device=dev) if N > 1 else None
             self.episode_idx = torch.zeros(B, dtype=torch.int32, device=dev)
             self.min_sep = torch.zeros(B, dtype=f32, device=dev) if track_min_sep else None
             self.stats = torch.zeros(_native.STAT_SLOTS, _native.STAT_FIELDS, dtype=torch.int64, device=dev)
-            # ---- per-step outputs (overwritten by every step)
-            self.obs = torch.zeros(B, L, dtype=f32, device=dev)
-            self.reward = torch.zeros(B, dtype=f32, device=dev)
-            self.done_u8 = torch.zeros(B, dtype=torch.uint8, device=dev)
-            self.flags = torch.zeros(B, dtype=torch.uint8, device=dev)
-            self.outcome = torch.zeros(B, dtype=torch.uint8, device=dev)
-            self.term_obs = torch.zeros(B, L, dtype=f32, device=dev)
-            self.ep_return = torch.zeros(B, dtype=f32, device=dev)
-            self.ep_length = torch.zeros(B, dtype=torch.int32, device=dev)
+            # ---- per-step outputs (overwritten by every step): ONE packed allocation, so that the host-buffer
+            #      step of a small batch moves everything with a single device-to-host copy
+            self._layout, self._out_bytes = self._packed_layout(B, L)
+            self._out = torch.zeros(self._out_bytes, dtype=torch.uint8, device=dev)
+            for name, (off, nbytes, dtype, shape) in self._layout.items():
+                setattr(self, name, self._out[off:off + nbytes].view(dtype).view(shape))
         self._state = State(
             num_envs=B, ppos=self.ppos.data_ptr(), paux=self.paux.data_ptr(), thot=self.thot.data_ptr(),
             tres=self.tres.data_ptr(), episode_idx=self.episode_idx.data_ptr(),
@@ -105,6 +102,20 @@ class BatchedACAS2D:
         self.launches = 0          # kernels launched through this object
 
     # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _packed_layout(B: int, L: int):
+        """Sections of the packed per-step output buffer, each 256-byte aligned: the small per-env arrays first,
+        then obs, then term_obs (so a prefix of the buffer holds everything but the terminal rows)."""
+        sections = (("reward", torch.float32, (B,)), ("done_u8", torch.uint8, (B,)), ("flags", torch.uint8, (B,)),
+                    ("outcome", torch.uint8, (B,)), ("ep_return", torch.float32, (B,)), ("ep_length", torch.int32, (B,)),
+                    ("obs", torch.float32, (B, L)), ("term_obs", torch.float32, (B, L)))
+        layout, off = {}, 0
+        for name, dtype, shape in sections:
+            n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+            layout[name] = (off, n, dtype, shape)
+            off = (off + n + 255) & ~255
+        return layout, max(off, 256)
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -178,25 +189,32 @@ class BatchedACAS2D:
             self.obs.copy_(obs[K - 1]); self.reward.copy_(reward[K - 1]); self.done_u8.copy_(done[K - 1])
         return obs, reward, done.view(torch.bool)
 
+    PACKED_HOST_LIMIT = 262144       # envs: below this the host-buffer step is latency-bound -> one packed D2H copy
+
     def host_buffers(self) -> Dict[str, np.ndarray]:
         """Pinned host staging buffers of ``step_host`` as numpy views: ``actions`` float32[B] (write
         your actions here and call ``step_host()`` to skip the pageable->pinned copy), ``obs``,
-        ``reward``, ``done``."""
+        ``reward``, ``done`` and -- valid where ``done`` -- ``term_obs``, ``ep_return``, ``ep_length``,
+        ``outcome``, plus ``flags``.  All but ``actions`` are sections of one pinned block that mirrors the
+        packed device block."""
         if self._host is None:
-            B, L = self.num_envs, self.obs_dim
-            self._host = dict(
-                actions=torch.zeros(B, dtype=torch.float32).pin_memory(),
-                obs=torch.zeros(B, L, dtype=torch.float32).pin_memory(),
-                reward=torch.zeros(B, dtype=torch.float32).pin_memory(),
-                done=torch.zeros(B, dtype=torch.uint8).pin_memory())
+            B = self.num_envs
+            self._host_actions = torch.zeros(B, dtype=torch.float32).pin_memory()
+            self._host_out = torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory()
+            self._host = {name: self._host_out[off:off + n].view(dtype).view(shape)
+                          for name, (off, n, dtype, shape) in self._layout.items()}
+            self._host["actions"] = self._host_actions
+            self._host["done"] = self._host["done_u8"]
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
         return self._host_np
 
     def step_host(self, actions: Optional[np.ndarray] = None):
         """Host-buffer step (the end-to-end path): ``actions`` float32[B] in host memory (``None`` =
         already written into ``host_buffers()["actions"]``) -> (obs float32[B, L], reward float32[B],
-        done bool[B]) numpy views of pinned buffers.  The H2D copy, the kernel, the three D2H copies
-        and one stream sync happen inside the call (chunk-pipelined over streams for large batches)."""
+        done bool[B]) numpy views of pinned buffers.  The H2D copy, the kernel, the D2H copies and one
+        stream sync happen inside the call: small batches move the whole packed output block (terminal rows
+        and finished-episode records included) with ONE copy; large batches are chunk-pipelined over streams
+        and copy obs / reward / done only."""
         hb = self.host_buffers()
         h = self._host
         a_ptr = h["actions"].data_ptr()
@@ -206,12 +224,23 @@ class BatchedACAS2D:
         elif actions is not None:
             np.copyto(hb["actions"], np.asarray(actions, dtype=np.float32).reshape(-1))
         with torch.cuda.device(self.device):
-            _native.check(self.lib.acas2d_step_host(
-                self._p(), self._s(), a_ptr, h["obs"].data_ptr(), h["reward"].data_ptr(),
-                h["done"].data_ptr(), self._actions_dev.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-                self.done_u8.data_ptr(), ctypes.byref(self._aux_full), self._stream()), "acas2d_step_host")
+            if self.num_envs <= self.PACKED_HOST_LIMIT:
+                _native.check(self.lib.acas2d_step_host_packed(
+                    self._p(), self._s(), a_ptr, self._actions_dev.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+                    self.done_u8.data_ptr(), ctypes.byref(self._aux_full), self._out.data_ptr(), self._host_out.data_ptr(),
+                    self._out_bytes, self._stream()), "acas2d_step_host_packed")
+            else:
+                _native.check(self.lib.acas2d_step_host(
+                    self._p(), self._s(), a_ptr, h["obs"].data_ptr(), h["reward"].data_ptr(),
+                    h["done"].data_ptr(), self._actions_dev.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+                    self.done_u8.data_ptr(), ctypes.byref(self._aux_full), self._stream()), "acas2d_step_host")
         self.launches += 1
         return hb["obs"], hb["reward"], hb["done"].view(np.bool_)
+
+    @property
+    def host_records_valid(self) -> bool:
+        """True when ``step_host`` also brings terminal rows / episode records to the host buffers."""
+        return self.num_envs <= self.PACKED_HOST_LIMIT
 
     # ------------------------------------------------------------------ synthetic rollouts
     def random_actions(self, step_index: int, action_seed: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -411,8 +440,9 @@ class BatchedACAS2D:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Checkpoint of the env batch (the reference never saves env state)."""
         d = {k: getattr(self, k).detach().clone() for k in self._STATE_TENSORS}
-        if self.min_sep is not None:
-            d["min_sep"] = self.min_sep.clone()
+        for k in ("min_sep", "tkin", "tpsi0"):
+            if getattr(self, k) is not None:
+                d[k] = getattr(self, k).clone()
         d["meta"] = torch.tensor([self.num_envs, self.n_traffic, self.seed, self.env_id_offset], dtype=torch.int64)
         return d
 
@@ -422,8 +452,13 @@ class BatchedACAS2D:
             raise ValueError("state_dict was taken from a batch of a different shape")
         for k in self._STATE_TENSORS:
             getattr(self, k).copy_(d[k])
-        if self.min_sep is not None and "min_sep" in d:
-            self.min_sep.copy_(d["min_sep"])
+        for k in ("min_sep", "tkin", "tpsi0"):
+            if getattr(self, k) is not None:
+                if k not in d:
+                    if k == "min_sep":
+                        continue
+                    raise ValueError(f"state_dict lacks '{k}' (taken by an older version): re-inject the state instead")
+                getattr(self, k).copy_(d[k])
 
     # ------------------------------------------------------------------ episode statistics
     def episode_counters(self) -> torch.Tensor:

@@ -51,7 +51,7 @@ class ACAS2DEnv(_EnvBase):
         d = bool(done[0])
         if d:
             g.running = False
-            g.outcome = int(self._core.outcome[0].item())
+            g.outcome = int(self._core.host_buffers()["outcome"][0])     # came with the step's one packed copy
             if self._verbose:
                 from gym_ACAS2D.settings import OUTCOME_NAMES
                 print("Outcome: {:<10} - Time steps: {:<10} - Total Reward: {}".format(

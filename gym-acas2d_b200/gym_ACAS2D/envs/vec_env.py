@@ -28,7 +28,7 @@ except Exception:                                      # noqa: BLE001
 
 class ACAS2DVecEnv(_VecEnvBase):
     def __init__(self, num_envs: int, n_traffic: Optional[int] = None, device="cuda", seed: Optional[int] = None,
-                 env_id_offset: int = 0, track_min_sep: bool = False, settings=None):
+                 env_id_offset: int = 0, track_min_sep: bool = False, settings=None, copy: bool = True):
         self.core = BatchedACAS2D(num_envs, n_traffic=n_traffic, device=device, seed=seed,
                                   env_id_offset=env_id_offset, auto_reset=True, track_min_sep=track_min_sep,
                                   settings=settings)
@@ -39,7 +39,10 @@ class ACAS2DVecEnv(_VecEnvBase):
         else:
             self.num_envs, self.observation_space, self.action_space = int(num_envs), obs_space, act_space
         self._pending: Optional[np.ndarray] = None
-        self._fin = None                               # pinned staging of finished-episode data
+        self._copy = bool(copy)
+        self._empty: List[dict] = [{} for _ in range(self.num_envs)]     # one (reused) empty info dict per env
+        self._infos: List[dict] = list(self._empty)
+        self._dirty: List[int] = []                                      # envs whose entry is not their empty dict
         self.metadata = {"render.modes": []}
 
     # ------------------------------------------------------------------ SB3 numpy surface
@@ -47,41 +50,41 @@ class ACAS2DVecEnv(_VecEnvBase):
         return self.core.reset().cpu().numpy()
 
     def step_async(self, actions: np.ndarray) -> None:
-        self._pending = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)[:, 0]
+        a = np.asarray(actions, dtype=np.float32)
+        self._pending = a.reshape(self.num_envs, -1)[:, 0] if a.ndim > 1 else a
 
     def step_wait(self):
+        """SB3 1.1.0 ``DummyVecEnv.step_wait`` semantics: fresh obs / rewards / dones arrays (``copy=False`` at
+        construction returns the pinned staging views instead) and one info dict per env -- empty unless the
+        env finished, then ``terminal_observation``, ``episode`` = {r, l} (Monitor) and ``outcome``."""
         if self._pending is None:
             raise RuntimeError("step_wait() without step_async()")
-        obs, reward, done = self.core.step_host(self._pending)
+        core = self.core
+        obs, reward, done = core.step_host(self._pending)
         self._pending = None
-        infos: List[dict] = [{} for _ in range(self.num_envs)]
+        infos = self._infos
+        for i in self._dirty:                          # last step's finished envs: back to their empty dict
+            infos[i] = self._empty[i]
         idx = np.flatnonzero(done)
-        if idx.size:
-            # finished episodes: the small per-env arrays whole, the terminal rows gathered, all four copies
-            # queued into pinned buffers behind one synchronisation
-            core, n = self.core, int(idx.size)
-            if self._fin is None:
-                B, L = self.num_envs, core.obs_dim
-                self._fin = dict(ret=torch.empty(B, dtype=torch.float32).pin_memory(),
-                                 length=torch.empty(B, dtype=torch.int32).pin_memory(),
-                                 outcome=torch.empty(B, dtype=torch.uint8).pin_memory(),
-                                 term=torch.empty(B, L, dtype=torch.float32).pin_memory(),
-                                 sel=torch.empty(B, dtype=torch.int64).pin_memory())
-            f = self._fin
-            f["sel"][:n] = torch.from_numpy(idx)
-            sel = f["sel"][:n].to(core.device, non_blocking=True)
-            f["term"][:n].copy_(core.term_obs.index_select(0, sel), non_blocking=True)
-            f["ret"].copy_(core.ep_return, non_blocking=True)
-            f["length"].copy_(core.ep_length, non_blocking=True)
-            f["outcome"].copy_(core.outcome, non_blocking=True)
-            torch.cuda.current_stream(core.device).synchronize()
-            term = f["term"][:n].numpy().copy()
-            ep_r, ep_l, oc = f["ret"].numpy(), f["length"].numpy(), f["outcome"].numpy()
-            for k, i in enumerate(idx):
+        self._dirty = idx.tolist()
+        if self._dirty:
+            if core.host_records_valid:                # the packed host block already holds rows and records
+                hb = core.host_buffers()
+                term, ep_r, ep_l, oc = hb["term_obs"][idx], hb["ep_return"][idx], hb["ep_length"][idx], hb["outcome"][idx]
+            else:                                      # large batch: gather the finished envs' rows on the device
+                sel = torch.from_numpy(idx).to(core.device, non_blocking=True)
+                term = core.term_obs.index_select(0, sel).cpu().numpy()
+                ep_r = core.ep_return.index_select(0, sel).cpu().numpy()
+                ep_l = core.ep_length.index_select(0, sel).cpu().numpy()
+                oc = core.outcome.index_select(0, sel).cpu().numpy()
+            ep_r, ep_l, oc = ep_r.tolist(), ep_l.tolist(), oc.tolist()
+            for k, i in enumerate(self._dirty):
                 infos[i] = {"terminal_observation": term[k],
-                            "episode": {"r": float(ep_r[i]), "l": int(ep_l[i]) - 1},   # l = step() calls
-                            "outcome": int(oc[i])}
-        return obs.copy(), reward.copy(), done.copy(), infos
+                            "episode": {"r": ep_r[k], "l": ep_l[k] - 1},     # l = step() calls
+                            "outcome": oc[k]}
+        if self._copy:
+            return obs.copy(), reward.copy(), done.copy(), list(infos)
+        return obs, reward, done, infos
 
     def step(self, actions: np.ndarray):
         self.step_async(actions)

@@ -183,6 +183,14 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state,
                      float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
                      const acas2d_step_aux *aux, void *stream);
 
+/* Host-buffer step for small (latency-bound) batches: the caller keeps obs / reward / done and every aux array
+ * inside ONE device block [d_packed, d_packed + packed_bytes); after the step the whole block goes to the pinned
+ * host block h_packed with a single copy (terminal rows and finished-episode records included), then the stream
+ * is synchronised.  obs / reward / done / aux are the device pointers the step writes (inside the block). */
+int acas2d_step_host_packed(const acas2d_params *params, const acas2d_state *state, const float *h_actions,
+                            float *d_actions, float *obs, float *reward, uint8_t *done, const acas2d_step_aux *aux,
+                            const void *d_packed, void *h_packed, int64_t packed_bytes, void *stream);
+
 /* State injection / extraction (the reference's tests poke game.player / game.traffic
  * attributes directly).  player double[B][3] = x, y, psi; traffic
  * double[B][N][4] = x, y, v_air, psi (CURRENT position); steps int32[B] = game.steps;

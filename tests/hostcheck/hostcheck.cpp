@@ -144,6 +144,8 @@ void hostcheck_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
 
 double hostcheck_wrap360(double t) { return wrap360(t); }
 
+void hostcheck_sincos_deg(double deg, double *s, double *c) { sincos_deg(deg, s, c); }
+
 void hostcheck_policy_mean(const float *weights, const float *obs, int64_t B, float *mean)
 {
     for (int64_t i = 0; i < B; ++i) mean[i] = policy_mean(weights, obs + 8 * i);

@@ -346,7 +346,8 @@ def test_properties_at_full_size(cuda):
         assert bool((obs >= lo).all()) and bool((obs <= 1.0011).all())
         shaped = rew - 1000.0 * ((f & 2) != 0) + 1000.0 * ((f & 1) != 0)
         assert float(shaped.min()) >= -2e-3 and float(shaped.max()) <= 1.0 + 1e-4
-    ex_steps = env.paux.view(torch.int32)[:, 2]
+    from gym_ACAS2D.envs import _native
+    ex_steps = env.paux.view(torch.int32)[:, 2] & _native.STEPS_MASK          # the word's top bits are record flags
     assert int(ex_steps.min()) >= 1 and int(ex_steps.max()) <= 1001
 
 
