@@ -122,7 +122,12 @@ inline DevParams make_dev_params(const acas2d_params &p)
     d.n_traffic = p.n_traffic;
     d.max_steps = (int32_t)p.max_steps;
     d.auto_reset = p.auto_reset;
-    d.q3_trivial = (p.airspeed_factor_min == 1.0 && p.airspeed_factor_max == 1.0) ? 1 : 0;
+    // spawned speeds are rounded to float32 (records): "exactly AIRSPEED" also needs AIRSPEED to survive that
+    d.q3_trivial = (p.airspeed_factor_min == 1.0 && p.airspeed_factor_max == 1.0 &&
+                    (double)(float)p.airspeed == p.airspeed) ? 1 : 0;
+    const double sure = 2.0 * p.collision_radius - 0.05;
+    d.coll_sure_d2 = sure > 0.0 ? (float)(sure * sure) : 0.0f;
+    d.dt_f = (float)dt;
     return d;
 }
 
@@ -260,6 +265,39 @@ ACAS_HD TrafficRec spawn_traffic(const DevParams &P, uint64_t seed, uint64_t gid
     return t;
 }
 
+// Spawn of intruder j with its records written and its reset-observation encounter returned: what
+// spawn_traffic + traffic_store + intruder_at(k = 0) + kin_store + encounter do, bit for bit, without the
+// float32 <-> float64 round trips in between (each one occupies the conversion pipe for as long as four DFMAs).
+ACAS_HD Encounter spawn_intruder(const DevParams &P, const StatePtrs &S, uint64_t gid, uint32_t episode, int j,
+                                 const Spawn0 &sp, const Player &rp, int64_t ij)
+{
+    Float4 h;
+    if (j == 0) { h.x = (float)sp.x; h.y = (float)sp.y; h.z = (float)sp.psi; h.w = (float)sp.v; }
+    else {
+        const U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), episode, (uint32_t)j,
+                                   (uint32_t)S.seed, (uint32_t)(S.seed >> 32));
+        h.x = P.tn_x_span_f * u01f(r.x);                                   // game.py:109-114, as spawn_slot
+        h.y = P.tn_y_span_f * u01f(r.y);
+        h.w = fmaf(P.factor_span_f, u01f(r.z), P.factor_min_f) * P.airspeed_f;
+        h.z = 360.0f * u01f(r.w);
+    }
+    S.thot[ij] = h;
+    TrafficRec tr;
+    tr.x0 = (double)h.x; tr.y0 = (double)h.y; tr.psi = (double)h.z;
+    tr.v = P.q3_trivial ? P.airspeed : (double)h.w;                        // == (double)h.w: the factor is exactly 1
+    double sn, cs;
+    sincos_deg(tr.psi, &sn, &cs);
+    Intruder it;
+    it.dx = (tr.v * cs) * P.dt; it.dy = (tr.v * sn) * P.dt; it.dyq = (P.airspeed * sn) * P.dt;
+    it.x = tr.x0; it.y = tr.y0;
+    if (S.tkin != nullptr) {
+        TrafficKin q;
+        q.x0 = h.x; q.y0 = h.y; q.dx = it.dx; q.dy = it.dy;
+        S.tkin[ij] = q;
+    }
+    return encounter(P, rp, it);
+}
+
 // ---------------------------------------------------------------- N_TRAFFIC == 1
 struct Env1 {
     double px, py, psi;
@@ -315,7 +353,7 @@ ACAS_HD void respawn_env1(const DevParams &P, const StatePtrs &S, Env1 &e, int64
     const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
     Player p;
     p.x = P.player_x0; p.y = P.player_y0;
-    player_set_heading(P, p, sp.player_psi, 0.0);                          // a_lat = 0 in a new game
+    player_set_heading_straight(p, sp.player_psi);                          // a_lat = 0 in a new game
     e.tr = spawn_traffic(P, S.seed, gid, episode, 0, sp);
     const Intruder t = intruder_at(P, e.tr, 0.0);
     const PlayerView v1 = player_view(P, p, 1);
@@ -509,7 +547,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             const uint64_t gid = S.gid0 + (uint64_t)i;
             const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
             p.x = P.player_x0; p.y = P.player_y0;
-            player_set_heading(P, p, sp.player_psi, 0.0);
+            player_set_heading_straight(p, sp.player_psi);
             const PlayerView v1 = player_view(P, p, 1);
 #pragma unroll
             for (int q = 0; q < 5; ++q) row[q] = v1.obs[q];
@@ -548,7 +586,7 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
     Player p;
     p.x = P.player_x0; p.y = P.player_y0;
-    player_set_heading(P, p, sp.player_psi, 0.0);
+    player_set_heading_straight(p, sp.player_psi);
     const PlayerView v = player_view(P, p, 1);
     float *row = obs ? obs + (int64_t)L * i : nullptr;
     if (row) for (int q = 0; q < 5; ++q) row[q] = v.obs[q];

@@ -22,6 +22,7 @@
 #include <cuda_pipeline.h>
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -41,6 +42,16 @@ using namespace acas2d;
 std::atomic<int64_t> g_launches{0};
 
 constexpr int kBlock = 256;
+
+// SM count of the CURRENT device (cached per device, not per process: one process may drive several GPUs)
+int sm_count()
+{
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sms[dev & 63] == 0) cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev & 63];
+}
 
 int check_args(const acas2d_params *p, const acas2d_state *s)
 {
@@ -255,11 +266,10 @@ int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, 
     constexpr int kTileEnvs = TILE;
     const bool compact = compact_ok(P, S) && (((uintptr_t)S.tpsi0) & 15) == 0;
     const int stage_bytes = TILE * (16 + 16 + (compact ? 4 : 16) + 4);
-    static int sms = 0;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     if (!attr_set[dev & 63]) {                      // function attributes are per device
         cudaFuncSetAttribute(step_n1_tma_kernel<STAGES, OCC, TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              STAGES * TILE * 52 + 64);
@@ -654,20 +664,27 @@ struct HostPipe {
     cudaEvent_t start, done[3];
     bool ok = false;
 };
-HostPipe &host_pipe()
+// One pipe per device (streams and events belong to the device that was current when they were created), and one
+// caller at a time per device: the pipe's streams are shared state.
+std::mutex g_pipe_mutex[64];
+HostPipe &host_pipe(int dev)
 {
-    static HostPipe p = [] {
-        HostPipe q;
+    static HostPipe pipes[64];
+    static bool made[64] = {};
+    HostPipe &q = pipes[dev & 63];
+    if (!made[dev & 63]) {
         q.ok = true;
         for (int i = 0; i < 3; ++i) {
             q.ok = q.ok && cudaStreamCreateWithFlags(&q.s[i], cudaStreamNonBlocking) == cudaSuccess;
             q.ok = q.ok && cudaEventCreateWithFlags(&q.done[i], cudaEventDisableTiming) == cudaSuccess;
         }
         q.ok = q.ok && cudaEventCreateWithFlags(&q.start, cudaEventDisableTiming) == cudaSuccess;
-        return q;
-    }();
-    return p;
+        made[dev & 63] = true;
+    }
+    return q;
 }
+
+
 constexpr int64_t kHostChunk = 256 * 1024;     // envs per chunk (multiple of the 256-env TMA tile)
 }  // namespace
 
@@ -684,7 +701,14 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t err;
 #define ACAS_TRY(call) do { err = (call); if (err != cudaSuccess) return (int)err; } while (0)
-    HostPipe *pipe = (B >= 2 * kHostChunk) ? &host_pipe() : nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::unique_lock<std::mutex> pipe_lock(g_pipe_mutex[dev & 63], std::defer_lock);
+    HostPipe *pipe = nullptr;
+    if (B >= 2 * kHostChunk) {
+        pipe_lock.lock();
+        pipe = &host_pipe(dev);
+    }
     if (!pipe || !pipe->ok) {
         ACAS_TRY(cudaMemcpyAsync(d_actions, h_actions, sizeof(float) * B, cudaMemcpyHostToDevice, st));
         if (int e = acas2d_step(params, state, d_actions, d_obs, d_reward, d_done, aux, stream)) return e;
@@ -868,12 +892,7 @@ int acas2d_policy_step_dyn(const acas2d_params *params, const acas2d_state *stat
     const DevParams P = make_dev_params(*params);
     const StatePtrs S = make_state_ptrs(*state);
     const Sinks out = make_sinks(obs_out, reward, done, aux);
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = sm_count();
     cudaStream_t st = (cudaStream_t)stream;
     if (int e = policy_prepare_device()) return e;
     if (tensor_cores) {
@@ -916,12 +935,7 @@ int acas2d_ppo_values(const float *params, const float *obs, int64_t n, float *v
     if (n < 0) return ACAS2D_E_BAD_SIZE;
     if (n == 0) return 0;
     if (!params || !obs || !values) return ACAS2D_E_NULL;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = sm_count();
     if (int e = ppo_prepare_device()) return e;
     long long grid = (long long)sms * 2;
     const long long tiles = (n + kPpoValTile - 1) / kPpoValTile;
@@ -1038,9 +1052,18 @@ int acas2d_ppo_step(const acas2d_ppo_config *cfg, float *params, const float *ob
     cudaStream_t st = (cudaStream_t)stream;
     const int ctas = launch_ppo_grad(cfg, params, obs, actions, old_logp, advantages, returns, indices, minibatch,
                                      workspace, sync, st);
-    ppo_update_kernel<<<kPpoUpdateCtas, kPpoUpdateThreads, 0, st>>>(params, workspace + ACAS2D_PPO_WORKSPACE_HEAD, ctas, cfg->ent_coef,
-                                                      1.0f / (float)minibatch, workspace, peers, rank, world, adam_m, adam_v,
-                                                      sync, make_adam(*cfg), loss_stats, grad_out);
+    // cooperative: the update kernel's CTAs meet at grid barriers, so they must all be resident together -- the
+    // driver guarantees it or refuses the launch (also inside a stream capture: the graph node keeps the attribute)
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(kPpoUpdateCtas); lc.blockDim = dim3(kPpoUpdateThreads); lc.dynamicSmemBytes = 0; lc.stream = st;
+    cudaLaunchAttribute coop;
+    coop.id = cudaLaunchAttributeCooperative;
+    coop.val.cooperative = 1;
+    lc.attrs = &coop; lc.numAttrs = 1;
+    const cudaError_t lerr = cudaLaunchKernelEx(&lc, ppo_update_kernel, params, (const float *)(workspace + ACAS2D_PPO_WORKSPACE_HEAD),
+                                                ctas, cfg->ent_coef, 1.0f / (float)minibatch, workspace, peers, (int)rank, (int)world,
+                                                adam_m, adam_v, sync, make_adam(*cfg), loss_stats, grad_out);
+    if (lerr != cudaSuccess) return (int)lerr;
     return finish_launch(2);
 }
 

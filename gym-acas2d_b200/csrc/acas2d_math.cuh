@@ -71,6 +71,8 @@ struct DevParams {
     // ---- integers
     int32_t n_traffic, max_steps, auto_reset;
     int32_t q3_trivial;     // every spawned intruder flies at exactly AIRSPEED (factor min == max == 1): Q3's term == dy
+    float coll_sure_d2;     // (2*COLLISION_RADIUS - 0.05)^2: a float32 separation estimate below this IS a collision
+    float dt_f;
 };
 
 // forward: used by sincos_deg below
@@ -314,6 +316,15 @@ ACAS_HD void player_set_heading(const DevParams &P, Player &p, double psi, doubl
     }
     p.cl = p.c * cd - p.s * sd;
     p.sl = p.s * cd + p.c * sd;
+}
+
+// The same for a new game: a_lat = 0, so the look-ahead heading IS the heading (game.py:88-92, kinematics.py:57-60).
+ACAS_HD void player_set_heading_straight(Player &p, double psi)
+{
+    p.psi = psi;
+    sincos_deg(psi, &p.s, &p.c);
+    p.cl = p.c;
+    p.sl = p.s;
 }
 
 ACAS_HD void player_advance(const DevParams &P, Player &p)

@@ -531,19 +531,28 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
 // counter, `target` = arrivals expected once every CTA has reached this barrier instance.
 // SYSTEM: the fence that publishes this CTA's stores (ordered before it by the bar.sync) is system-scope, so
 // that a peer GPU which later observes this rank's release flag also observes them.
+// The launch is COOPERATIVE (cudaLaunchAttributeCooperative: the driver either makes all CTAs resident together or
+// fails the launch), and every spin is BOUNDED: a barrier or a peer flag that does not come within ~10 s -- a dead
+// or late peer rank -- records ACAS2D_PPO_ERR_* in sync[1] and lets the kernel finish instead of hanging the GPU;
+// the host reads the word back (FusedLearner.check()).
+constexpr unsigned kPpoSpinLimit = 1u << 25;
 template <bool SYSTEM = false>
-__device__ __forceinline__ void ppo_grid_barrier(unsigned long long *counter, const unsigned long long target)
+__device__ __forceinline__ void ppo_grid_barrier(unsigned long long *counter, const unsigned long long target, int32_t *err)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         if (SYSTEM) __threadfence_system(); else __threadfence();
         atomicAdd(counter, 1ull);
-        while (ld_acquire_gpu_u64(counter) < target) {}
+        unsigned spins = 0;
+        while (ld_acquire_gpu_u64(counter) < target) {
+            if (++spins > kPpoSpinLimit) { atomicExch(err, ACAS2D_PPO_ERR_BARRIER); break; }
+            __nanosleep(64);
+        }
     }
     __syncthreads();
 }
 
-// sync: int32[4] = { Adam step (incremented by ppo_grad_kernel), spare, 64-bit barrier-arrival counter }.  The
+// sync: int32[4] = { Adam step (incremented by ppo_grad_kernel), error word (0 = ok), 64-bit barrier-arrival counter }.  The
 // counter is only ever advanced by this kernel, by exactly gridDim.x * barriers_per_step per launch, so its value
 // at launch (rounded down: early CTAs of the same launch may already have arrived) numbers the launch -- the
 // barrier targets, the exchange-buffer parity and the peer flags all derive from that sequence number, not from
@@ -581,12 +590,16 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
         const int half = (int)(seq & 1u) * kPpoParams;      // double-buffered: a fast rank's next step cannot overwrite
         float *mine = peers.block[rank];                   // what a slow peer is still reading
         if (owner) mine[half + p] = g;
-        ppo_grid_barrier<true>(arrivals, arrivals_before + gridDim.x);    // the whole gradient of this rank is published
+        ppo_grid_barrier<true>(arrivals, arrivals_before + gridDim.x, sync + 1);    // the whole gradient of this rank is published
         if (blockIdx.x == 0 && t < world)
             st_release_sys_u32((unsigned *)(peers.block[t] + kPpoXFlags) + rank, seq);
         if (t < world) {
             const unsigned *flag = (const unsigned *)(mine + kPpoXFlags) + t;
-            while ((int)(ld_acquire_sys_u32(flag) - seq) < 0) {}
+            unsigned spins = 0;
+            while ((int)(ld_acquire_sys_u32(flag) - seq) < 0) {
+                if (++spins > kPpoSpinLimit) { atomicExch(sync + 1, ACAS2D_PPO_ERR_PEER); break; }
+                __nanosleep(64);
+            }
         }
         __syncthreads();
         if (owner) {
@@ -605,7 +618,7 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
     // 3. global norm: one partial per CTA, barrier, every CTA sums the 38 partials in the same order
     const float q = ppo_block_sum(owner ? g * g : 0.0f, red);
     if (t == 0) norm_parts[blockIdx.x] = q;
-    ppo_grid_barrier(arrivals, arrivals_before + per_launch);
+    ppo_grid_barrier(arrivals, arrivals_before + per_launch, sync + 1);
     if (t < 32) {                                          // 38 partials: lanes take c and c + 32, fixed shuffle tree
         float x = 0.0f;
         for (int c = t; c < (int)gridDim.x; c += 32) x += __ldcg(norm_parts + c);

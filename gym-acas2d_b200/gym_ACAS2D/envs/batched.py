@@ -435,7 +435,9 @@ class BatchedACAS2D:
             out["min_sep"] = self.min_sep.cpu().numpy()
         return out
 
-    _STATE_TENSORS = ("ppos", "paux", "thot", "tres", "episode_idx", "stats")
+    # the games AND the per-step buffers: policy_step / collect_rollout read ``obs`` as the actor's input, so a
+    # resumed closed-loop rollout needs it (it cannot be rebuilt exactly: the row depends on the last action)
+    _STATE_TENSORS = ("ppos", "paux", "thot", "tres", "episode_idx", "stats", "obs", "reward", "done_u8")
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Checkpoint of the env batch (the reference never saves env state)."""
@@ -450,6 +452,10 @@ class BatchedACAS2D:
         meta = d["meta"].tolist()
         if meta[0] != self.num_envs or meta[1] != self.n_traffic:
             raise ValueError("state_dict was taken from a batch of a different shape")
+        if meta[2] != self.seed or meta[3] != self.env_id_offset:
+            # respawns are Philox(seed, global env id, episode): adopt the checkpoint's stream, or they diverge
+            self.seed, self.env_id_offset = int(meta[2]), int(meta[3])
+            self._state.seed, self._state.env_id_offset = self.seed, self.env_id_offset
         for k in self._STATE_TENSORS:
             getattr(self, k).copy_(d[k])
         for k in ("min_sep", "tkin", "tpsi0"):

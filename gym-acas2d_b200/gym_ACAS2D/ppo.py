@@ -361,7 +361,18 @@ class FusedLearner:
             for k in range(self.minibatches):
                 self._step(k)
 
+    def check(self) -> None:
+        """Raises if the update kernel recorded a timed-out grid barrier / peer flag (``sync[1]``, see
+        ``acas2d_ppo_step``): the kernel's spins are bounded, so a dead or late peer rank ends in this error
+        instead of a hung GPU."""
+        code = int(self.sync[1].item())
+        if code:
+            what = {1: "a grid barrier of the update kernel timed out",
+                    2: "a peer rank's gradient did not arrive (dead or late rank)"}.get(code, f"error {code}")
+            raise RuntimeError(f"FusedLearner: {what}; the last update is invalid")
+
     def logged(self) -> Dict[str, float]:
+        self.check()
         s = self.loss_stats.tolist()
         return dict(policy_loss=s[0], value_loss=s[1], approx_kl=s[2], clip_fraction=s[3], grad_norm=s[4])
 
@@ -402,13 +413,20 @@ class TorchLearner:
                     adam_step=torch.as_tensor(step).detach().reshape(1).to(torch.int64).cpu())
 
     def load_state_dict(self, d: Dict[str, torch.Tensor]) -> None:
+        """Resume.  Existing optimiser-state tensors are overwritten IN PLACE: a CUDA graph captured by ``bind``
+        keeps updating those storages, so replacing them would silently drop the restored moments."""
         with torch.no_grad():
             self.params.copy_(d["params"])
-        capturable = self.device.type == "cuda"
-        step = d["adam_step"].reshape(()).to(torch.float32)
-        self.opt.state[self.params] = dict(step=step.to(self.device) if capturable else step.cpu(),
-                                           exp_avg=d["adam_m"].to(self.device).clone(),
-                                           exp_avg_sq=d["adam_v"].to(self.device).clone())
+            capturable = self.device.type == "cuda"
+            step = d["adam_step"].reshape(()).to(torch.float32)
+            st = self.opt.state.get(self.params)
+            if st and all(k in st for k in ("step", "exp_avg", "exp_avg_sq")):
+                st["exp_avg"].copy_(d["adam_m"]); st["exp_avg_sq"].copy_(d["adam_v"])
+                st["step"].copy_(step) if torch.is_tensor(st["step"]) else st.__setitem__("step", step.cpu())
+            else:
+                self.opt.state[self.params] = dict(step=step.to(self.device) if capturable else step.cpu(),
+                                                   exp_avg=d["adam_m"].to(self.device).clone(),
+                                                   exp_avg_sq=d["adam_v"].to(self.device).clone())
 
     def values(self, obs, out=None):
         with torch.no_grad():
@@ -458,15 +476,18 @@ class TorchLearner:
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
-                saved = (self.params.detach().clone(), self.opt.state_dict())
-                for _ in range(3):                                          # warm-up (allocations, Adam state)
+                # the warm-up (allocations, Adam state creation) must neither train nor lose a resumed state:
+                # parameters and the optimiser moments / step count are put back afterwards, into the same storages
+                prior = self.opt.state.get(self.params)
+                saved_params = self.params.detach().clone()
+                saved_state = {k: v.detach().clone() for k, v in prior.items() if torch.is_tensor(v)} if prior else None
+                for _ in range(3):
                     self._body()
-                with torch.no_grad():                                       # the warm-up must not train
-                    self.params.copy_(saved[0])
-                for st in self.opt.state.values():
-                    for v in st.values():
+                with torch.no_grad():
+                    self.params.copy_(saved_params)
+                    for k, v in self.opt.state[self.params].items():
                         if torch.is_tensor(v):
-                            v.zero_()
+                            v.copy_(saved_state[k]) if saved_state is not None and k in saved_state else v.zero_()
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)

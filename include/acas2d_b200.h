@@ -307,7 +307,9 @@ int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *gr
 /* One whole gradient step in two kernels: the gradient of acas2d_ppo_grad, then -- fused in one kernel --
  * the fixed-order reduction, the data-parallel gradient exchange, clip_grad_norm_ and the Adam step.
  * sync int32[4] (16-byte aligned), zero-initialised, owned by the learner: [0] = Adam step count (incremented
- * here), [2..3] = a 64-bit count of barrier arrivals that numbers the launches of the update kernel (its grid
+ * here), [1] = error word (0, or ACAS2D_PPO_ERR_* once a grid barrier / a peer's flag did not arrive within the
+ * kernel's bounded spin -- the update of that step is then invalid; the kernel never hangs),
+ * [2..3] = a 64-bit count of barrier arrivals that numbers the launches of the update kernel (its grid
  * barriers, the exchange-buffer parity and the peer flags derive from it, not from the step count, so this call
  * may be mixed with acas2d_ppo_grad / acas2d_ppo_adam on the same learner).
  * grad_out float[PARAM_FLOATS] or NULL: the (averaged) gradient that was applied, before clipping.
@@ -317,7 +319,11 @@ int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *gr
  * (zero-initialised) mapped into this process (CUDA IPC / VMM symmetric memory; NVLink peer access).  Each
  * rank publishes its gradient in its own block (double-buffered by step parity), signals every peer with a
  * release store, waits for all peers' signals and sums the blocks in rank order -- every rank applies the
- * bit-identical mean gradient and no NCCL call is made.  world == 1: rank 0, peer_exchange NULL. */
+ * bit-identical mean gradient and no NCCL call is made.  world == 1: rank 0, peer_exchange NULL.
+ * The update kernel is a COOPERATIVE launch (its CTAs wait on each other): if the device cannot hold all of them
+ * at once the call returns the launch error (cudaErrorCooperativeLaunchTooLarge) instead of dead-locking. */
+#define ACAS2D_PPO_ERR_BARRIER 1   /* sync[1]: a grid barrier of the update kernel timed out */
+#define ACAS2D_PPO_ERR_PEER    2   /* sync[1]: a peer rank's gradient flag did not arrive */
 int acas2d_ppo_step(const acas2d_ppo_config *cfg, float *params, const float *obs, const float *actions,
                     const float *old_logp, const float *advantages, const float *returns, const int64_t *indices,
                     int64_t minibatch, float *workspace, float *adam_m, float *adam_v, int32_t *sync,

@@ -472,6 +472,31 @@ def test_state_dict_roundtrip(cuda):
         assert torch.equal(oa, b.step(act)[0])
 
 
+def test_state_dict_resumes_a_closed_loop_rollout(cuda, golden_dir):
+    """Checkpoint in the middle of a policy-driven rollout: the actor's next input is the ``obs`` buffer, so the
+    checkpoint must carry it (and the Philox stream identity: seed, env id offset).  The resumed batch -- built
+    with another seed and offset on purpose -- continues bit for bit."""
+    from gym_ACAS2D.policy import MlpActor
+    actor = MlpActor.from_file(os.path.join(golden_dir, "ppo_policy_1048576_11.npz"), "cuda:0")
+    a = make(2048, 1, seed=8, env_id_offset=4096, auto_reset=True)
+    a.reset()
+    ex = a.extract_state()
+    ex["steps"][:] = 1 + (np.arange(2048) * 13) % 990                  # episodes end (and respawn) along the way
+    a.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    a.observe()
+    for t in range(40):
+        a.policy_step(actor, deterministic=False, noise_seed=3, step_index=t)
+    sd = a.state_dict()
+    b = make(2048, 1, seed=99, env_id_offset=0, auto_reset=True)
+    b.load_state_dict(sd)
+    for t in range(40, 80):
+        oa, ra, da = a.policy_step(actor, deterministic=False, noise_seed=3, step_index=t)
+        ob, rb, db = b.policy_step(actor, deterministic=False, noise_seed=3, step_index=t)
+        assert torch.equal(oa.view(torch.int32), ob.view(torch.int32)) and torch.equal(ra, rb) and torch.equal(da, db)
+    assert torch.equal(a.episode_idx, b.episode_idx) and torch.equal(a.paux, b.paux)
+    assert int(a.episode_counters()[0]) > 50
+
+
 def test_gym_surface_single_env(cuda):
     """The reference's gym API (environment.py:8-54): spaces, reset -> float64[8], 4-tuple step,
     env.game attributes; and an episode replayed through the oracle from the extracted state."""

@@ -323,6 +323,41 @@ def test_learner_checkpoint_resume_across_learners():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("order", ["load_then_bind", "bind_then_load"])
+def test_torch_learner_resume_with_cuda_graph(order):
+    """TorchLearner with cuda_graph=True (the default on CUDA): a checkpoint loaded BEFORE bind() must survive
+    bind()'s warm-up, and one loaded AFTER bind() must reach the storages the captured graph updates.  Either
+    way the resumed learner continues like the one that never stopped."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    dev = "cuda:0"
+    cfg = PpoConfig.sb3_defaults()
+    n, mbs = 4096, 4
+    data = synthetic_rollout(n, seed=8, device=dev)
+
+    def run_epochs(L, k):
+        torch.manual_seed(123)                              # same minibatch permutations for both learners
+        for _ in range(k):
+            L.epoch()
+
+    a = ppo.TorchLearner(dev, cfg, init_state_dict(), cuda_graph=True)
+    a.bind(*data, mbs)
+    run_epochs(a, 2)
+    ckpt = {k: v.clone() for k, v in a.state_dict().items()}
+    assert int(ckpt["adam_step"]) == 2 * mbs
+    b = ppo.TorchLearner(dev, cfg, init_state_dict(seed=77), cuda_graph=True)
+    if order == "load_then_bind":
+        b.load_state_dict(ckpt); b.bind(*data, mbs)
+    else:
+        b.bind(*data, mbs); b.load_state_dict(ckpt)
+    assert int(b.state_dict()["adam_step"]) == 2 * mbs
+    assert torch.equal(b.state_dict()["adam_m"], ckpt["adam_m"]) and torch.equal(b.params.detach(), ckpt["params"])
+    run_epochs(a, 2); run_epochs(b, 2)
+    assert int(b.state_dict()["adam_step"]) == 4 * mbs
+    assert float((a.params.detach() - b.params.detach()).abs().max()) < 1e-6
+
+
+@pytest.mark.gpu
 def test_ppo_training_loop_fused_learner():
     """Short end-to-end run on the fused learner: finite statistics, the policy moves, episodes finish."""
     if not torch.cuda.is_available():
