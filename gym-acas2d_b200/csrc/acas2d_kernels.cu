@@ -452,9 +452,14 @@ int launch_tiled_as(const DevParams &P, const StatePtrs &S, const float *actions
 }
 
 template <int G>
-int launch_tiled(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
+int launch_tiled(const DevParams &P, const StatePtrs &S0, const float *actions, const Sinks &out, cudaStream_t st)
 {
-    const bool kin = tiled_use_kin(S, P.n_traffic);
+    // When the cache is not the record of choice for this batch, the step does not maintain it either: respawned
+    // envs get no cache entry and lose their "cache valid" bit (a later launch that prefers the cache takes the
+    // records for them) -- at N = 256, where nearly every env respawns every step, that is 24 of 52 bytes written.
+    const bool kin = tiled_use_kin(S0, P.n_traffic);
+    StatePtrs S = S0;
+    if (!kin) S.tkin = nullptr;
     if (S.min_sep) return kin ? launch_tiled_as<G, true, true>(P, S, actions, out, st) : launch_tiled_as<G, true, false>(P, S, actions, out, st);
     return kin ? launch_tiled_as<G, false, true>(P, S, actions, out, st) : launch_tiled_as<G, false, false>(P, S, actions, out, st);
 }
@@ -638,8 +643,10 @@ int acas2d_step(const acas2d_params *params, const acas2d_state *state, const fl
             else step_n1_kernel<false, 3><<<grid, kBlock, 0, st>>>(P, S, actions, out);
         }
     } else if (tuning().force_loop) {
-        if (S.min_sep) step_loop_kernel<true><<<grid, kBlock, 0, st>>>(P, S, actions, out);
-        else step_loop_kernel<false><<<grid, kBlock, 0, st>>>(P, S, actions, out);
+        StatePtrs Sl = S;
+        if (!tiled_use_kin(S, P.n_traffic)) Sl.tkin = nullptr;      // same record policy as the tiled kernel (below)
+        if (S.min_sep) step_loop_kernel<true><<<grid, kBlock, 0, st>>>(P, Sl, actions, out);
+        else step_loop_kernel<false><<<grid, kBlock, 0, st>>>(P, Sl, actions, out);
     } else {
         int rc = 0;
         switch (tiled_group(P.n_traffic)) {

@@ -60,7 +60,7 @@ inline size_t tiled_smem_bytes(int N, int G, bool kin)
 {
     const int E = 32 / G, L = 5 + 3 * N;
     const size_t tile = ((size_t)E * tiled_row_stride(N, G, kin) * (kin ? 24 : 16) + 15) & ~(size_t)15;
-    const size_t otile = ((size_t)E * L * 4 + 15) & ~(size_t)15;
+    const size_t otile = (((size_t)E * L * 4 + 15) & ~(size_t)15) + 16;      // + one 16-byte word: the span's phase (see 7.)
     return kTiledWarps * (tile + otile);
 }
 
@@ -157,9 +157,8 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
     const int TS = tiled_row_stride(N, G, KIN);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile_bytes = ((size_t)E * TS * REC + 15) & ~(size_t)15;
-    const size_t warp_bytes = tile_bytes + (((size_t)E * L * 4 + 15) & ~(size_t)15);
+    const size_t warp_bytes = tile_bytes + (((size_t)E * L * 4 + 15) & ~(size_t)15) + 16;
     unsigned char *tile = smem_raw + warp * warp_bytes;
-    float *otile = (float *)(tile + tile_bytes);
     __shared__ uint64_t tile_bar[kTiledWarps];                               // one mbarrier per warp (TMA tile copy)
 
     const int64_t env0 = ((int64_t)blockIdx.x * kTiledWarps + warp) * E;      // first env of this warp
@@ -169,6 +168,10 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
     const bool valid = e < nvalid;
     const int64_t env = env0 + (valid ? e : 0);
     const bool lead = valid && sub == 0;
+    // the warp's observation rows are one contiguous span of HBM; the tile is laid out with the span's own phase
+    // within a 16-byte word, so that everything but <= 3 floats at either end goes out as one TMA bulk store
+    const int64_t span0 = env0 * L;
+    float *otile = (float *)(tile + tile_bytes) + (int)(span0 & 3);
 
     // 1. stage the traffic tile
     if (nvalid > 0) {
@@ -432,17 +435,19 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         }
         __syncwarp();
 
-        // 7. coalesced write-back: the rows of the warp's consecutive envs are one contiguous span of
-        //    HBM and of the (unpadded) observation tile; 128-bit stores when the span is 16-byte aligned
-        const int64_t span0 = env0 * L;
-        const int span = nvalid * L;
-        if (((span0 | span) & 3) == 0) {
+        // 7. coalesced write-back of the span: scalar stores up to the first 16-byte boundary, one TMA bulk store for
+        //    the aligned body, scalar stores for the rest
+        {
+            const int span = nvalid * L;
+            int head = (4 - (int)(span0 & 3)) & 3;
+            if (head > span) head = span;
+            const int body = (span - head) & ~3, tail = span - head - body;
+            float *dst = out.obs + span0;
             fence_proxy_async_shared();                                     // the lanes' shared writes, for the bulk engine
             __syncwarp();
-            if (lane == 0) tma_store_1d_and_wait(out.obs + span0, smem_u32(otile), (unsigned)span * 4u);
-        } else {
-            float *dst = out.obs + span0;
-            for (int c = lane; c < span; c += 32) __stcs(dst + c, otile[c]);
+            if (lane == 0 && body > 0) tma_store_1d_and_wait(dst + head, smem_u32(otile + head), (unsigned)body * 4u);
+            if (lane >= 8 && lane < 8 + head) __stcs(dst + (lane - 8), otile[lane - 8]);
+            if (lane >= 16 && lane < 16 + tail) __stcs(dst + head + body + (lane - 16), otile[head + body + (lane - 16)]);
         }
 
         if (lead) {
