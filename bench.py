@@ -598,6 +598,7 @@ def run_ours(args):
                 torch.randn(n_l, device=dev, generator=g)]
         res = {}
         for name in ("p2p", "nccl"):
+            torch.manual_seed(1234)                      # the same initial parameters on every rank
             learner = _ppo.FusedLearner(dev, None, None, cuda_graph=True, exchange=name)
             learner.bind(*data, mbs)
             learner.epoch()

@@ -85,6 +85,7 @@ inline DevParams make_dev_params(const acas2d_params &p)
     d.airspeed = p.airspeed;
     d.v_dt = p.airspeed * dt;
     d.dpsi_per_action = p.acc_lat_limit / p.airspeed;               // aircraft.py:20-22 (Q1)
+    d.acc_lat_limit = p.acc_lat_limit;
     d.lookahead_rad = dt * kDeg2Rad;                                // kinematics.py:57-59 (Q2)
     d.goal_x = p.goal_x; d.goal_y = p.goal_y;
     d.coll_d2 = (2.0 * p.collision_radius) * (2.0 * p.collision_radius);   // game.py:187
@@ -572,6 +573,91 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
     S.ppos[i] = np;
     S.paux[i] = na;
     if (MINSEP) S.min_sep[i] = minsep;
+}
+
+// ---------------------------------------------------------------- on-device episode records
+// The reference appends to per-step Python lists inside action() and evaluate() (game.py:45-75, 231-239,
+// 266-276; initial entries game.py:132-160) and its scripts dump them (testing_main.py:113-138).  Here a traced
+// env gets one row of ACAS2D_TRACE_DOUBLES (+ 2 per recorded intruder) float64 values per step in a ring buffer
+// in HBM.  trace_env runs BEFORE the step of the same actions and computes, without touching the state, the row
+// that step is about to produce; a game at steps == 1 (fresh from reset / respawn) first gets its initial row.
+struct TraceRing {
+    int64_t first_env, num_envs;
+    int32_t capacity, n_traffic_rec;
+    int32_t *cursor;
+    double *rows;
+};
+
+ACAS_HD void trace_row(const DevParams &P, const TraceRing &T, int64_t w, const Player &p, int steps, double a_lat,
+                       double d_sep, const PlayerView &v, const Encounter &e0, float reward, int flags, bool initial,
+                       const double *txy, int nrec)
+{
+    const int stride = ACAS2D_TRACE_DOUBLES + 2 * T.n_traffic_rec;
+    const int c = T.cursor[w];
+    T.cursor[w] = c + 1;
+    double *r = T.rows + ((int64_t)w * T.capacity + (c % T.capacity)) * stride;
+    const RewardTerms t = reward_terms(P, v, e0);
+    r[0] = p.x; r[1] = p.y; r[2] = p.psi; r[3] = a_lat; r[4] = d_sep;
+    r[5] = (double)v.d_goal; r[6] = (double)t.dh; r[7] = (double)(e0.v_c * P.fps); r[8] = (double)e0.d_cpa;
+    r[9] = (double)v.d_dev; r[10] = (double)t.r_goal; r[11] = (double)t.r_head; r[12] = (double)t.r_cpa;
+    r[13] = (double)t.r_dev;
+    r[14] = initial ? (double)t.r5 : (double)(t.r5 * (1.0f - (float)steps * P.inv_max_steps));   // game.py:159 / 262-263
+    r[15] = (double)steps; r[16] = (double)reward; r[17] = (double)flags;
+    for (int j = 0; j < nrec; ++j) { r[ACAS2D_TRACE_DOUBLES + 2 * j] = txy[2 * j]; r[ACAS2D_TRACE_DOUBLES + 2 * j + 1] = txy[2 * j + 1]; }
+}
+
+ACAS_HD void trace_env(const DevParams &P, const StatePtrs &S, const TraceRing &T, int64_t w, const float *actions)
+{
+    const int64_t i = T.first_env + w;
+    const int N = P.n_traffic;
+    const int nrec = T.n_traffic_rec < N ? T.n_traffic_rec : N;
+    const Vec2d pp = S.ppos[i];
+    const PlayerAux pa = S.paux[i];
+    const bool residual = (pa.steps & kResidualBit) != 0;
+    const int k = pa.steps & kStepsMask;
+    double txy[2 * ACAS2D_TRACE_MAX_TRAFFIC];
+    Player p;
+    if (k == 1) {
+        // initial records of a new game (game.py:132-160): current state, a_lat = 0, no time discount
+        p.x = pp.x; p.y = pp.y;
+        player_set_heading_straight(p, pa.psi);
+        const PlayerView v = player_view(P, p, k);
+        Encounter e0;
+        double sep2 = INFINITY;
+        for (int j = 0; j < N; ++j) {
+            const Intruder t = intruder_at(P, traffic_load(S, i * N + j, residual), 0.0);
+            if (j < nrec) { txy[2 * j] = t.x; txy[2 * j + 1] = t.y; }
+            const Encounter en = encounter(P, p, t);
+            if (j == 0) e0 = en;
+            sep2 = fmin(sep2, en.d2);
+        }
+        trace_row(P, T, w, p, k, 0.0, sqrt(sep2), v, e0, 0.0f, 0, true, txy, nrec);
+    }
+    const float action = actions[i];
+    const double dpsi = (double)action * P.dpsi_per_action;
+    p.x = pp.x; p.y = pp.y;
+    player_set_heading(P, p, wrap360(pa.psi + dpsi), dpsi);
+    player_advance(P, p);
+    const int steps = k + 1;
+    const PlayerView v = player_view(P, p, steps);
+    Encounter e0;
+    bool coll = false;
+    double sep2 = INFINITY;
+    for (int j = 0; j < N; ++j) {
+        const Intruder t = intruder_at(P, traffic_load(S, i * N + j, residual), (double)k);
+        const double ox = (t.x - t.dx) - p.x, oy = (t.y - t.dy) - p.y;       // Q10: records see the OLD traffic
+        if (j < nrec) { txy[2 * j] = t.x - t.dx; txy[2 * j + 1] = t.y - t.dy; }
+        sep2 = fmin(sep2, ox * ox + oy * oy);
+        const Encounter en = encounter(P, p, t);
+        if (j == 0) e0 = en;
+        coll |= en.d2 < P.coll_d2;
+    }
+    const bool goal = v.dg2 < P.goal_r2, tout = steps > P.max_steps;
+    float r = shaped_reward(P, p, v, e0, steps);
+    r += (coll ? P.reward_collision : 0.0f) + (goal ? P.reward_goal : 0.0f);
+    const int flags = (coll ? ACAS2D_FLAG_COLLISION : 0) | (goal ? ACAS2D_FLAG_GOAL : 0) | (tout ? ACAS2D_FLAG_TIMEOUT : 0) |
+                      ((coll || goal || tout) ? ACAS2D_FLAG_DONE : 0);
+    trace_row(P, T, w, p, steps, (double)action * P.acc_lat_limit, sqrt(sep2), v, e0, r, flags, false, txy, nrec);
 }
 
 // ---------------------------------------------------------------- reset / inject / extract

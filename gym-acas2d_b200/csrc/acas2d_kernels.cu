@@ -531,6 +531,13 @@ render_kernel(const DevParams P, const StatePtrs S, const int64_t env, const int
     rgb[3 * pix + 0] = r; rgb[3 * pix + 1] = g; rgb[3 * pix + 2] = b;
 }
 
+__global__ void __launch_bounds__(128)
+trace_kernel(const DevParams P, const StatePtrs S, const TraceRing T, const float *__restrict__ actions)
+{
+    const int64_t w = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (w < T.num_envs) trace_env(P, S, T, w, actions);
+}
+
 __global__ void __launch_bounds__(kBlock)
 random_actions_kernel(int64_t B, uint64_t gid0, uint64_t action_seed, uint64_t step_index, float *__restrict__ actions)
 {
@@ -781,6 +788,25 @@ int acas2d_step_host_packed(const acas2d_params *params, const acas2d_state *sta
     err = cudaMemcpyAsync(h_packed, d_packed, (size_t)packed_bytes, cudaMemcpyDeviceToHost, st);
     if (err != cudaSuccess) return (int)err;
     return (int)cudaStreamSynchronize(st);
+}
+
+int acas2d_trace_step(const acas2d_params *params, const acas2d_state *state, const float *actions,
+                      const acas2d_trace *trace, void *stream)
+{
+    if (int e = check_args(params, state)) return e;
+    if (!trace || !actions) return ACAS2D_E_NULL;
+    if (trace->num_envs == 0) return 0;
+    if (!trace->cursor || !trace->rows) return ACAS2D_E_NULL;
+    if (trace->first_env < 0 || trace->num_envs < 0 || trace->first_env + trace->num_envs > state->num_envs ||
+        trace->capacity < 2 || trace->n_traffic_rec < 0 || trace->n_traffic_rec > ACAS2D_TRACE_MAX_TRAFFIC ||
+        trace->n_traffic_rec > params->n_traffic)
+        return ACAS2D_E_BAD_SIZE;
+    TraceRing T;
+    T.first_env = trace->first_env; T.num_envs = trace->num_envs; T.capacity = trace->capacity;
+    T.n_traffic_rec = trace->n_traffic_rec; T.cursor = trace->cursor; T.rows = trace->rows;
+    trace_kernel<<<(unsigned)((T.num_envs + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        make_dev_params(*params), make_state_ptrs(*state), T, actions);
+    return finish_launch();
 }
 
 int acas2d_inject_state(const acas2d_params *params, const acas2d_state *state, const double *player,

@@ -41,6 +41,7 @@ struct DevParams {
     // ---- float64 flag chain
     double v_dt;            // AIRSPEED / FPS: player displacement per step (aircraft.py:25-26)
     double dpsi_per_action; // ACC_LAT_LIMIT / AIRSPEED: heading change [deg] per unit action (Q1)
+    double acc_lat_limit;   // game.py:225 (episode records only)
     double lookahead_rad;   // (1/FPS) * pi/180: closing_speed's look-ahead turn per degree of dpsi (Q2)
     double goal_x, goal_y;  // game.py:80-81
     double coll_d2;         // (2*COLLISION_RADIUS)^2, game.py:187
@@ -400,15 +401,16 @@ ACAS_HD PlayerView player_view(const DevParams &P, const Player &p, int32_t step
     return v;
 }
 
-// step_reward_5 (rewards.py:53-60) with intruder 0 only (Q7), times the time discount (Q6).
-ACAS_HD float shaped_reward(const DevParams &P, const Player &p, const PlayerView &v,
-                            const Encounter &e0, int32_t steps)
+// The terms of step_reward_5 (rewards.py:5-60) with intruder 0 only (Q7).
+struct RewardTerms { float dh, r_head, r_cpa, r_dev, r_goal, r5; };
+
+ACAS_HD RewardTerms reward_terms(const DevParams &P, const PlayerView &v, const Encounter &e0)
 {
-    (void)p;
+    RewardTerms t;
     // delta_heading (kinematics.py:82-83) from the float32 heading / bearing (error < 5e-5 deg)
     const float a = fabsf(v.obs[1] * 360.0f - v.phi_deg);
-    const float dh = fminf(a, 360.0f - a);
-    float h = 1.0f - dh * (1.0f / 180.0f);
+    t.dh = fminf(a, 360.0f - a);
+    float h = 1.0f - t.dh * (1.0f / 180.0f);
     h = h * h; h = h * h;                                    // rewards.py:7
     // v_closing <= 0 branch (rewards.py:55-57)
     float c = e0.d_cpa * P.inv_safe_distance;                // rewards.py:16
@@ -420,8 +422,18 @@ ACAS_HD float shaped_reward(const DevParams &P, const Player &p, const PlayerVie
     float g = 1.0f - v.d_goal * P.inv_rw_goal_max;           // rewards.py:48
     g = g * g; g = g * g;
     g = fminf(1.0f, g);
-    const float r = (e0.v_c <= 0.0f) ? h * c * dv : h * g;   // rewards.py:54 (NaN -> else, as in Python)
-    return r * (1.0f - (float)steps * P.inv_max_steps);      // game.py:262-263
+    t.r_head = h; t.r_dev = dv; t.r_goal = g;
+    t.r_cpa = (e0.v_c > 0.0f) ? 1.0f : c;                    // rewards.py:13: 1 when separating (Q4)
+    t.r5 = (e0.v_c <= 0.0f) ? h * c * dv : h * g;            // rewards.py:54 (NaN -> else, as in Python)
+    return t;
+}
+
+// step_reward_5 times the time discount (Q6).
+ACAS_HD float shaped_reward(const DevParams &P, const Player &p, const PlayerView &v,
+                            const Encounter &e0, int32_t steps)
+{
+    (void)p;
+    return reward_terms(P, v, e0).r5 * (1.0f - (float)steps * P.inv_max_steps);      // game.py:262-263
 }
 
 // ------------------------------------------------------------------ spawn (game.py:85-116)

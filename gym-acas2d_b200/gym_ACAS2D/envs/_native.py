@@ -44,7 +44,7 @@ EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
            "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render",
            "acas2d_ppo_values", "acas2d_ppo_gae", "acas2d_ppo_grad", "acas2d_ppo_adam", "acas2d_ppo_step",
-           "acas2d_ppo_prepare", "acas2d_policy_step_dyn", "acas2d_step_k", "acas2d_set_tiled_tuning", "acas2d_step_host_packed")
+           "acas2d_ppo_prepare", "acas2d_policy_step_dyn", "acas2d_step_k", "acas2d_set_tiled_tuning", "acas2d_step_host_packed", "acas2d_trace_step")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -85,6 +85,17 @@ class PpoConfig(ctypes.Structure):
         return cls(**d)
 
 
+TRACE_DOUBLES, TRACE_MAX_TRAFFIC = 18, 16
+TRACE_FIELDS = ("x", "y", "psi", "a_lat", "d_sep", "d_goal", "delta_heading", "v_closing", "d_cpa", "d_dev", "r_d_goal",
+                "r_h_goal", "r_d_cpa", "r_d_dev", "r_step", "steps", "reward", "flags")
+
+
+class Trace(ctypes.Structure):
+    """``acas2d_trace``: ring buffers of per-step episode records for a window of envs."""
+    _fields_ = [("first_env", ctypes.c_int64), ("num_envs", ctypes.c_int64), ("capacity", ctypes.c_int32),
+                ("n_traffic_rec", ctypes.c_int32), ("cursor", ctypes.c_void_p), ("rows", ctypes.c_void_p)]
+
+
 class StepAux(ctypes.Structure):
     """``acas2d_step_aux``: optional per-step outputs."""
     _fields_ = [("flags", ctypes.c_void_p), ("outcome", ctypes.c_void_p), ("term_obs", ctypes.c_void_p),
@@ -115,6 +126,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_step_k.argtypes = [PP, SP, ctypes.c_int32, vp, vp, vp, vp, AP, vp]
     lib.acas2d_step_host.argtypes = [PP, SP, vp, vp, vp, vp, vp, vp, vp, vp, AP, vp]
     lib.acas2d_step_host_packed.argtypes = [PP, SP, vp, vp, vp, vp, vp, AP, vp, vp, ctypes.c_int64, vp]
+    lib.acas2d_trace_step.argtypes = [PP, SP, vp, ctypes.POINTER(Trace), vp]
     lib.acas2d_inject_state.argtypes = [PP, SP, vp, vp, vp, vp, vp]
     lib.acas2d_extract_state.argtypes = [PP, SP, vp, vp, vp, vp, vp]
     lib.acas2d_rollout_random.argtypes = [PP, SP, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, vp, vp]

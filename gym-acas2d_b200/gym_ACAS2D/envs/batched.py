@@ -98,6 +98,7 @@ class BatchedACAS2D:
         self._aux_lean = StepAux(flags=None, outcome=self.outcome.data_ptr(), term_obs=None,
                                  ep_return=self.ep_return.data_ptr(), ep_length=self.ep_length.data_ptr())
         self._host = None          # pinned staging buffers of step_host
+        self._trace = None         # on-device episode records (enable_trace)
         self._actions_dev = torch.zeros(B, dtype=f32, device=dev)
         self.launches = 0          # kernels launched through this object
 
@@ -153,6 +154,36 @@ class BatchedACAS2D:
         self.launches += 1
         return self.obs
 
+    # ------------------------------------------------------------------ on-device episode records
+    def enable_trace(self, num_envs: Optional[int] = None, first_env: int = 0, capacity: Optional[int] = None,
+                     n_traffic_rec: Optional[int] = None) -> None:
+        """Record per-step episode data (the reference's per-step lists, game.py:45-75) for the window
+        ``[first_env, first_env + num_envs)`` into ring buffers in HBM: ``capacity`` rows per env (default
+        MAX_STEPS + 2, a whole episode).  ``step`` / ``step_host`` then launch the trace kernel before the step
+        kernel (``acas2d_trace_step``); read with ``trace_rows()``.  ``policy_step`` / ``rollout_random`` /
+        ``step_k`` choose or hold their actions inside the kernel and are not traced."""
+        E = self.num_envs - first_env if num_envs is None else int(num_envs)
+        cap = int(self.params.max_steps) + 2 if capacity is None else int(capacity)
+        nrec = min(self.n_traffic, _native.TRACE_MAX_TRAFFIC) if n_traffic_rec is None else int(n_traffic_rec)
+        width = _native.TRACE_DOUBLES + 2 * nrec
+        self._trace_rows = torch.zeros(E, cap, width, dtype=torch.float64, device=self.device)
+        self._trace_cursor = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self._trace = _native.Trace(first_env=int(first_env), num_envs=E, capacity=cap, n_traffic_rec=nrec,
+                                    cursor=self._trace_cursor.data_ptr(), rows=self._trace_rows.data_ptr())
+
+    def disable_trace(self) -> None:
+        self._trace = None
+
+    def _trace_step(self, a_ptr: int) -> None:
+        _native.check(self.lib.acas2d_trace_step(self._p(), self._s(), a_ptr, ctypes.byref(self._trace), self._stream()),
+                      "acas2d_trace_step")
+        self.launches += 1
+
+    def trace_rows(self):
+        """(rows float64 [E, capacity, 18 + 2 n_rec], count int32 [E]) as numpy; row t of env w is
+        ``rows[w, t % capacity]``, fields ``_native.TRACE_FIELDS`` then the recorded intruders' x, y."""
+        return self._trace_rows.cpu().numpy(), self._trace_cursor.cpu().numpy()
+
     def step(self, actions, full_outputs: bool = True):
         """One environment step for all envs.  Returns views of the internal (obs, reward, done)
         buffers; they are overwritten by the next call.  With ``full_outputs`` the per-env
@@ -161,6 +192,8 @@ class BatchedACAS2D:
         a = self._as_actions(actions)
         aux = self._aux_full if full_outputs else self._aux_lean
         with torch.cuda.device(self.device):
+            if self._trace is not None:
+                self._trace_step(a.data_ptr())
             _native.check(self.lib.acas2d_step(self._p(), self._s(), a.data_ptr(), self.obs.data_ptr(),
                                                self.reward.data_ptr(), self.done_u8.data_ptr(),
                                                ctypes.byref(aux), self._stream()), "acas2d_step")
@@ -224,6 +257,10 @@ class BatchedACAS2D:
         elif actions is not None:
             np.copyto(hb["actions"], np.asarray(actions, dtype=np.float32).reshape(-1))
         with torch.cuda.device(self.device):
+            if self._trace is not None:                     # the trace kernel reads the actions on the device
+                src = actions if a_ptr != h["actions"].data_ptr() else h["actions"]
+                self._actions_dev.copy_(src.reshape(-1), non_blocking=True)
+                self._trace_step(self._actions_dev.data_ptr())
             if self.num_envs <= self.PACKED_HOST_LIMIT:
                 _native.check(self.lib.acas2d_step_host_packed(
                     self._p(), self._s(), a_ptr, self._actions_dev.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),

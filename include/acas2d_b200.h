@@ -191,6 +191,31 @@ int acas2d_step_host_packed(const acas2d_params *params, const acas2d_state *sta
                             float *d_actions, float *obs, float *reward, uint8_t *done, const acas2d_step_aux *aux,
                             const void *d_packed, void *h_packed, int64_t packed_bytes, void *stream);
 
+/* On-device episode records (reference: the per-step lists of game.py:45-75, appended at
+ * game.py:231-239 and 266-276, dumped by testing_main.py:113-138).  A window of envs gets one row of float64
+ * values per step in a ring buffer in HBM:
+ *   [0] x  [1] y  [2] psi  [3] a_lat  [4] d_sep (minimum separation, new player / OLD traffic, Q10)  [5] d_goal
+ *   [6] delta_heading  [7] v_closing  [8] d_cpa  [9] d_dev  [10] r_d_goal  [11] r_h_goal  [12] r_d_cpa  [13] r_d_dev
+ *   [14] r_step (shaped reward incl. time discount, no terminal bonus)  [15] game.steps after the step
+ *   [16] reward of the step  [17] ACAS2D_FLAG_* of the step;  then x, y of the first n_traffic_rec intruders as the
+ *   reference records them (before they move).  A game at steps == 1 first gets its initial row (a_lat = 0, no
+ *   discount, reward 0: game.py:132-160).
+ * acas2d_trace_step is called BEFORE acas2d_step with the same actions: it computes the rows that step is about to
+ * produce without touching the state (the hot kernels carry no tracing code).  cursor int32[num_envs] counts the
+ * rows written per env (row index = count % capacity); rows double[num_envs][capacity][18 + 2 n_traffic_rec]. */
+#define ACAS2D_TRACE_DOUBLES 18
+#define ACAS2D_TRACE_MAX_TRAFFIC 16
+typedef struct acas2d_trace {
+    int64_t  first_env;      /* traced window: envs [first_env, first_env + num_envs) of the batch */
+    int64_t  num_envs;
+    int32_t  capacity;       /* rows per env */
+    int32_t  n_traffic_rec;  /* intruders whose positions are recorded, <= min(n_traffic, ACAS2D_TRACE_MAX_TRAFFIC) */
+    int32_t *cursor;
+    double  *rows;
+} acas2d_trace;
+int acas2d_trace_step(const acas2d_params *params, const acas2d_state *state, const float *actions,
+                      const acas2d_trace *trace, void *stream);
+
 /* State injection / extraction (the reference's tests poke game.player / game.traffic
  * attributes directly).  player double[B][3] = x, y, psi; traffic
  * double[B][N][4] = x, y, v_air, psi (CURRENT position); steps int32[B] = game.steps;

@@ -606,6 +606,59 @@ def test_golden_csv_replayed_on_the_gpu(cuda, golden_dir):
         assert list(pd.read_csv(os.path.join(d, "b.csv")).columns) == records.BASELINE_COLUMNS
 
 
+def test_on_device_episode_records_match_the_reference_lists(cuda):
+    """SURVEY 8f-3 as specified: per-step records written by a kernel into ring buffers in HBM and read back once
+    (acas2d_trace_step), against the reference's per-step lists (game.py:45-75, 231-239, 266-276) as the oracle's
+    Python port keeps them -- random actions, N_TRAFFIC = 1 and 3, every recorded quantity."""
+    import random
+    from gym_ACAS2D import records
+    from oracle.acas2d_oracle import DEFAULTS, PyPortGame
+    for n in (1, 3):
+        consts = dict(DEFAULTS, MIN_TRAFFIC=n, MAX_TRAFFIC=n)
+        rng = random.Random(100 + n)
+        games = [PyPortGame(rng, consts) for _ in range(6)]
+        player = np.array([[g.player.x, g.player.y, g.player.psi] for g in games])
+        traffic = np.array([[[t.x, t.y, t.v_air, t.psi] for t in g.traffic] for g in games])
+        arng = np.random.default_rng(n)
+        acts = arng.uniform(-1, 1, (1001, 6)).astype(np.float32)
+        for b, g in enumerate(games):
+            g.observe()
+            for k in range(1001):
+                if g.step(np.array([float(acts[k, b])]))[2]:
+                    break
+        env = make(6, n, auto_reset=False)
+        step_no = {"k": 0}
+
+        def policy(obs):
+            a = torch.from_numpy(acts[step_no["k"]]).cuda()
+            step_no["k"] += 1
+            return a
+
+        rows = records.record_episodes(env, policy=policy, start=(player, traffic))
+        for b, (row, g) in enumerate(zip(rows, games)):
+            assert row["Time Steps"] == g.steps and row["Outcome"] == {1: "Goal", 2: "Collision", 3: "Timeout"}[g.outcome]
+            assert np.abs(np.array(row["Path"]) - np.array(g.path)).max() < 1e-9
+            for i in range(n):
+                assert np.abs(np.array(row["Traffic Paths"][i]) - np.array(g.traffic_paths[i])).max() < 1e-9
+            want = dict(psi=g.rec["psi"], d_sep=g.rec["sep"], a_lat=g.rec["a_lat"], d_goal=g.rec["d_goal"],
+                        delta_heading=g.rec["dh"], v_closing=g.rec["vc"], d_cpa=g.rec["dcpa"], d_dev=g.rec["ddev"],
+                        r_d_goal=g.rec["r_goal"], r_h_goal=g.rec["r_head"], r_d_cpa=g.rec["r_cpa"], r_d_dev=g.rec["r_dev"],
+                        r_step=g.rec["r"])
+            tol = dict(psi=1e-9, d_sep=2e-3, a_lat=2e-5, d_goal=2e-3, delta_heading=1e-4, v_closing=1e-3, d_cpa=5e-3,
+                       d_dev=1e-4, r_d_goal=2e-6, r_h_goal=2e-6, r_d_cpa=2e-5, r_d_dev=2e-5, r_step=2e-5)
+            for key, ref in want.items():
+                got, ref = np.array(row[key], np.float64), np.array(ref, np.float64)
+                assert got.shape == ref.shape, (key, got.shape, ref.shape)
+                near_branch = np.abs(np.array(g.rec["vc"])) < 1e-3          # r_d_cpa / r_step switch on v_closing's sign
+                d = np.abs(got - ref)
+                if key in ("r_d_cpa", "r_step"):
+                    d = np.where(near_branch, 0.0, d)
+                if key == "delta_heading":
+                    d = np.minimum(d, 360 - d)
+                assert np.nanmax(d) <= tol[key], (n, b, key, float(np.nanmax(d)))
+            assert abs(row["Total Reward"] - g.total_reward) < parity.TOL_RETURN
+
+
 def test_headless_render_frame(cuda):
     """debug frame of one env -- sky, goal disc + yellow GOAL_RADIUS ring, player disc + red
     COLLISION_RADIUS ring, intruder disc + ring, at the positions of the device state."""
