@@ -615,6 +615,27 @@ def run_ours(args):
                                             "every rank's gradient through NVLink peer memory (no NCCL call, whole epoch one "
                                             "CUDA graph) vs gradient -> NCCL all-reduce -> Adam"}
 
+    def leg_config5():
+        # BASELINE config 5: end-to-end PPO (rollout through the GPU VecEnv adapter + learner), SB3-default
+        # hyper-parameters of the reference's model (training_main.py:44-52), every rank 1024 envs x 256 steps per iteration
+        from gym_ACAS2D import ppo as _ppo
+        t0 = time.perf_counter()
+        hist = _ppo.train(num_envs=1024, n_steps=256, iterations=6, device=dev, seed=13, minibatches=64, n_epochs=10,
+                          tensor_cores=True, cuda_graph=True, learner="fused", exchange="p2p", log=None)
+        wall = time.perf_counter() - t0
+        steady = hist[2:]                                   # the first iterations carry graph captures
+        steps_it = 1024 * 256 * world
+        roll = sum(h["rollout_s"] for h in steady) / len(steady)
+        learn = sum(h["learn_s"] for h in steady) / len(steady)
+        other["config5_ppo_vecenv"] = {
+            "value": steps_it / (roll + learn), "unit": "env-steps/s (rollout + learning, whole job)", "ranks": world,
+            "rollout_env_steps_per_s": steps_it / roll, "rollout_s_per_iteration": roll, "learn_s_per_iteration": learn,
+            "gradient_steps_per_iteration": 640, "us_per_gradient_step": 1e6 * learn / 640, "wall_s_6_iterations": wall,
+            "param_divergence_over_ranks": getattr(_ppo.train, "param_divergence", None),
+            "note": "PPO from scratch through ACAS2DVecEnv.collect_rollout (fused tcgen05 actor + env step, one CUDA graph per "
+                    "rollout) and the fused learner; N ranks: gradient exchange inside the update kernel over NVLink peer memory. "
+                    "The reference's own run logged 69-89 env-steps/s (BASELINE.md)"}
+
     def leg_config3_strong():
         # BASELINE config 3 literally: 1 Mi envs split over the ranks (L2-resident shards: launch/latency-bound)
         total = 1 << 20
@@ -656,6 +677,8 @@ def run_ours(args):
         if world > 1:
             leg("config3_strong", leg_config3_strong)
             leg("ppo_p2p", leg_ppo_p2p)
+        if N == 1:
+            leg("config5", leg_config5)
         if world == 1 or args.sweep:
             leg("sweep", leg_sweep)
 

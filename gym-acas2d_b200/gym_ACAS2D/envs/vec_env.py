@@ -100,6 +100,15 @@ class ACAS2DVecEnv(_VecEnvBase):
         data for the rows where ``done`` is set."""
         return self.core.step(actions)
 
+    def collect_rollout(self, actor, n_steps: int, **kw):
+        """On-device counterpart of SB3's ``OnPolicyAlgorithm.collect_rollouts`` over this VecEnv (BASELINE
+        config 5): ``n_steps`` closed-loop steps of the fused actor + env-step kernel written straight into
+        [T, B] rollout buffers (``BatchedACAS2D.collect_rollout``); nothing crosses the host."""
+        return self.core.collect_rollout(actor, n_steps, **kw)
+
+    def episode_stats(self, reduce: bool = True):
+        return self.core.episode_stats(reduce=reduce)
+
     # ------------------------------------------------------------------ VecEnv plumbing
     def close(self) -> None:
         return None

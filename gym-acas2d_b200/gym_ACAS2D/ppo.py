@@ -537,8 +537,11 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
     rank, world = _world()
     cfg = PpoConfig.sb3_defaults(gamma=gamma, gae_lambda=gae_lambda, clip_range=clip_range, vf_coef=vf_coef,
                                  ent_coef=ent_coef, max_grad_norm=max_grad_norm, lr=lr)
-    env = BatchedACAS2D(num_envs, device=dev, seed=seed, auto_reset=True, env_id_offset=rank * num_envs)
-    env.reset()
+    # the GPU VecEnv adapter (BASELINE config 5: "PPO rollout via GPU VecEnv adapter"); its zero-copy tensor surface
+    from gym_ACAS2D.envs.vec_env import ACAS2DVecEnv
+    venv = ACAS2DVecEnv(num_envs, device=dev, seed=seed, env_id_offset=rank * num_envs)
+    venv.reset_tensor()
+    env = venv.core
     init = ActorCritic().sb3_state_dict()
     if learner == "fused":
         L = FusedLearner(dev, cfg, init, cuda_graph=cuda_graph, exchange=exchange)
@@ -555,8 +558,8 @@ def train(num_envs: int = 4096, n_steps: int = 128, iterations: int = 20, device
         actor = L.actor()
         env.clear_stats()
         t0 = time.perf_counter()
-        buffers = env.collect_rollout(actor, T, noise_seed=seed, step0=it * T, tensor_cores=tensor_cores, buffers=buffers,
-                                      graph=cuda_graph and learner == "fused")
+        buffers = venv.collect_rollout(actor, T, noise_seed=seed, step0=it * T, tensor_cores=tensor_cores, buffers=buffers,
+                                       graph=cuda_graph and learner == "fused")
         torch.cuda.synchronize(dev)
         t_roll = time.perf_counter() - t0
         stats = env.episode_stats(reduce=True)
