@@ -438,8 +438,8 @@ inline bool tiled_use_kin(const StatePtrs &S, int N)
 template <int G, bool MINSEP, bool KIN>
 int launch_tiled_as(const DevParams &P, const StatePtrs &S, const float *actions, const Sinks &out, cudaStream_t st)
 {
-    constexpr int E = 32 / G;
-    const size_t smem = tiled_smem_bytes(P.n_traffic, G, KIN);
+    constexpr int E = 32 / G, kTiledWarps = TiledShape<G>::kWarps;
+    const size_t smem = tiled_smem_bytes(P.n_traffic, G, KIN, kTiledWarps);
     const uint32_t magic_n = (uint32_t)((0x100000000ULL + (uint64_t)P.n_traffic - 1) / (uint64_t)P.n_traffic);   // idx / N for idx < 2^16
     const int64_t warps = (S.B + E - 1) / E;
     const unsigned grid = (unsigned)((warps + kTiledWarps - 1) / kTiledWarps);

@@ -31,7 +31,11 @@
 
 namespace acas2d {
 
-constexpr int kTiledWarps = 4;
+// Warps per CTA.  The warps of a CTA share nothing but the launch, and a warp with a respawning env runs about
+// twice as long as one without: single-warp CTAs give the SM its resources back warp by warp (measured, N = 64:
+// 41.2 -> 37.4 us at 65 536 envs, 136.8 -> 125.4 us at 262 144; N = 8, 16, 32 gain 1-5 %).  With one env per warp
+// (G == 32, N >= 256) every warp respawns and four-warp CTAs are better (211 vs 245 us).
+template <int G> struct TiledShape { static constexpr int kWarps = (G == 32) ? 4 : 1; };
 
 // What the player phase leaves for the lanes of an env.
 struct alignas(16) PlayerStage {
@@ -56,12 +60,12 @@ __host__ __device__ inline int tiled_row_stride(int N, int G, bool kin)
     return N;
 }
 
-inline size_t tiled_smem_bytes(int N, int G, bool kin)
+inline size_t tiled_smem_bytes(int N, int G, bool kin, int warps)
 {
     const int E = 32 / G, L = 5 + 3 * N;
     const size_t tile = ((size_t)E * tiled_row_stride(N, G, kin) * (kin ? 24 : 16) + 15) & ~(size_t)15;
     const size_t otile = (((size_t)E * L * 4 + 15) & ~(size_t)15) + 16;      // + one 16-byte word: the span's phase (see 7.)
-    return kTiledWarps * (tile + otile);
+    return warps * (tile + otile);
 }
 
 // float64 player update + player-only observation terms of one env (game.py:222-229, 199-203)
@@ -145,12 +149,14 @@ player_phase_kernel(const DevParams P, const StatePtrs S, const float *__restric
 #endif
 
 template <int G, bool MINSEP, bool KIN>
-__global__ void __launch_bounds__(kTiledWarps * 32, KIN ? ACAS2D_TILED_MIN_BLOCKS_KIN : ACAS2D_TILED_MIN_BLOCKS)
+__global__ void __launch_bounds__(TiledShape<G>::kWarps * 32,
+                                  (KIN ? ACAS2D_TILED_MIN_BLOCKS_KIN : ACAS2D_TILED_MIN_BLOCKS) * 4 / TiledShape<G>::kWarps)
 step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
                   const uint32_t magic_n)
 {
     constexpr int E = 32 / G;
     constexpr int REC = KIN ? 24 : 16;
+    constexpr int kTiledWarps = TiledShape<G>::kWarps;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.n_traffic;
     const int L = 5 + 3 * N;
