@@ -432,6 +432,9 @@ inline bool tiled_use_kin(const StatePtrs &S, int N)
     // measured (B200, fraction of the HBM roofline, cache vs records): N = 64 at 262 144 envs 0.61 vs 0.53, N = 256 at
     // 65 536 envs 0.35 vs 0.30, N = 8 at 65 536 envs 0.38 vs 0.33 -- but N = 8 at 1 Mi envs 0.67 vs 0.71: with few
     // intruders per env the step is HBM-bound once the cache no longer fits L2, and the cache is 8 bytes more per intruder
+    // N >= 256: one env per warp and (reference spawn rule) an episode per step -- a cache entry is written and read
+    // once; the records win (203 vs 210 us) and move 0.5 GB less per launch
+    if (N >= 256) return false;
     return N >= 16 || (double)S.B * N * 24.0 <= 48e6;
 }
 

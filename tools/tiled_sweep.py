@@ -23,6 +23,7 @@ peak, _ = bench.measured_peak()
 def timed(fn, iters):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(400000)
     e0.record()
     for k in range(iters):
         fn(k)
