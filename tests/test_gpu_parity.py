@@ -272,6 +272,41 @@ def test_tma_ring_kernel_equals_direct_kernel(cuda, stages, occ):
     assert a.episode_counters()[0].item() > 1000
 
 
+def test_deferred_respawn_queue_overflow(cuda):
+    """The persistent N == 1 kernel queues finished envs per CTA (256 slots) and respawns them after its last tile;
+    more than that in one launch -- here EVERY env of a 400 000-env batch times out on the same step, ~1350 per
+    CTA -- must take the in-line path and still equal the direct kernel bit for bit; then a second mass ending of
+    the freshly respawned (compact-record) games by collision-free timeouts again."""
+    from gym_ACAS2D.envs import _native
+    lib = _native.load()
+    B = 400_000 + 123
+    a = make(B, 1, seed=6, auto_reset=True); b = make(B, 1, seed=6, auto_reset=True)
+    a.reset(); b.reset()
+    try:
+        for rnd in range(2):
+            for e in (a, b):
+                ex = e.extract_state()
+                ex["steps"][:] = 1000                      # the next step is step() call number 1000: timeout (Q5)
+                if rnd == 1:
+                    ex["steps"][::2] = 999                 # ... half of them one step later
+                e.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+            for t in range(3):
+                act = a.random_actions(10 * rnd + t, 2)
+                lib.acas2d_set_n1_kernel(1, 2)
+                oa, ra, da = a.step(act)
+                lib.acas2d_set_n1_kernel(0, 0)
+                ob, rb, db = b.step(act)
+                assert torch.equal(oa.view(torch.int32), ob.view(torch.int32)) and torch.equal(ra, rb) and torch.equal(da, db)
+                assert torch.equal(a.term_obs[da], b.term_obs[db]) and torch.equal(a.outcome[da], b.outcome[db])
+                if t == 0:
+                    assert int(da.sum()) >= (B if rnd == 0 else B // 2)       # all (half) time out; a few also collide / land
+    finally:
+        lib.acas2d_set_n1_kernel(1, 2)
+    assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.thot, b.thot)
+    assert torch.equal(a.tpsi0, b.tpsi0) and torch.equal(a.episode_idx, b.episode_idx)
+    assert torch.equal(a.episode_counters(), b.episode_counters()) and int(a.episode_counters()[0]) >= 2 * B
+
+
 @pytest.mark.parametrize("stages,occ", [(2, 2), (5, 3)])
 def test_tma_ring_stress_at_full_size(cuda, stages, occ):
     """Regression for a cross-proxy WAR race: at 4 Mi envs every CTA refills each ring stage ~10 times
