@@ -210,9 +210,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 256                                   # env-steps per core per bench "step"
     K, W = args.steps, args.warmup
     K_eff = min(K, 400)                              # bounded: the whole run ends within minutes
+    per_step = max(256, -(-40000 // K_eff))          # env-steps per core per bench "step": >= 40 000 steps (~3 s) per core
     t0 = time.perf_counter()
     d = run_ref_runner(cores, per_step * K_eff, n_traffic=args.n_traffic, gate=6)
     if d.get("available") and d.get("gate", {}).get("ok") and "rate" in d:
