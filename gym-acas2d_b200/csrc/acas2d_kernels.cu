@@ -448,8 +448,19 @@ int launch_tiled_as(const DevParams &P, const StatePtrs &S, const float *actions
     const unsigned grid = (unsigned)((warps + kTiledWarps - 1) / kTiledWarps);
     cudaError_t err = cudaFuncSetAttribute(step_tiled_kernel<G, MINSEP, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    if (G > 1 && S.pstage)                      // the float64 player update, once per env, as its own launch
+    if (G > 1 && S.pstage) {                    // the float64 player update, once per env, as its own launch
         player_phase_kernel<<<(unsigned)((S.B + 127) / 128), 128, 0, st>>>(P, S, actions);
+        // ... and the tiled kernel as its PROGRAMMATIC dependent: it starts while the pre-pass runs (tile copies,
+        // index arithmetic) and waits for it only where it reads the scratch
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(kTiledWarps * 32); lc.dynamicSmemBytes = smem; lc.stream = st;
+        cudaLaunchAttribute pdl;
+        pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl.val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = &pdl; lc.numAttrs = 1;
+        err = cudaLaunchKernelEx(&lc, step_tiled_kernel<G, MINSEP, KIN>, P, S, actions, out, magic_n);
+        return err == cudaSuccess ? 0 : (int)err;
+    }
     step_tiled_kernel<G, MINSEP, KIN><<<grid, kTiledWarps * 32, smem, st>>>(P, S, actions, out, magic_n);
     return 0;
 }

@@ -134,6 +134,9 @@ __device__ __forceinline__ void stage_load(const Float4 *__restrict__ src, int64
 __global__ void __launch_bounds__(128)
 player_phase_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions)
 {
+    // programmatic dependent launch: the tiled kernel that follows may start now -- its tile copies do not depend
+    // on this kernel; it waits (griddepcontrol.wait) before it reads the scratch written here
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int64_t env = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (env >= S.B) return;
     PlayerStage ps;
@@ -213,6 +216,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
     PlayerStage ps;
     if (valid) {
         if (G > 1 && S.pstage) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");      // the pre-pass (launched just before) has completed
             stage_load(S.pstage, S.B, env, ps);
         } else {
             player_phase(P, S, actions, env, MINSEP, ps);
