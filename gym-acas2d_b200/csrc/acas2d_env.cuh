@@ -62,6 +62,7 @@ struct StatePtrs {
     TrafficKin *tkin;       // optional (N > 1)
     float *tpsi0;           // optional (N == 1)
     Float4 *pstage;         // optional scratch (N > 1): [7][B] 16-byte words
+    float *spawn_sep;       // optional (N > 1): minimum separation of the game at its spawn
 };
 
 struct Sinks {
@@ -129,6 +130,8 @@ inline DevParams make_dev_params(const acas2d_params &p)
     const double sure = 2.0 * p.collision_radius - 0.05;
     d.coll_sure_d2 = sure > 0.0 ? (float)(sure * sure) : 0.0f;
     d.dt_f = (float)dt;
+    d.vrel_step = (float)(p.airspeed * dt * (1.0 + p.airspeed_factor_max) * (1.0 + 1e-6));
+    d.coll_sure = (float)(2.0 * p.collision_radius - 1e-3);
     return d;
 }
 
@@ -148,6 +151,7 @@ inline StatePtrs make_state_ptrs(const acas2d_state &s)
     o.tkin = (TrafficKin *)s.tkin;
     o.tpsi0 = s.tpsi0;
     o.pstage = (Float4 *)s.pstage;
+    o.spawn_sep = s.spawn_sep;
     return o;
 }
 
@@ -566,6 +570,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             }
             steps_out = 1 | spawn_bits(P, S);
             ret = 0.0f;
+            if (S.spawn_sep) S.spawn_sep[i] = minsep;
         }
     }
     Vec2d np; np.x = p.x; np.y = p.y;
@@ -699,6 +704,7 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     S.ppos[i] = np;
     S.paux[i] = na;
     if (S.min_sep) S.min_sep[i] = minsep;
+    if (S.spawn_sep) S.spawn_sep[i] = minsep;
 }
 
 // game.observe() WITHOUT the steps increment (game.py:199-220): the observation row of the state as it
@@ -755,6 +761,7 @@ ACAS_HD void inject_env(const DevParams &P, const StatePtrs &S, int64_t i, const
     S.ppos[i] = np;
     S.paux[i] = na;
     if (S.min_sep) S.min_sep[i] = minsep;
+    if (S.spawn_sep) S.spawn_sep[i] = INFINITY;                    // not a spawn: no bound
 }
 
 ACAS_HD void extract_env(const DevParams &P, const StatePtrs &S, int64_t i, double *player, double *traffic,

@@ -761,6 +761,7 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
         sub.min_sep = state->min_sep ? state->min_sep + off : nullptr;
         sub.tkin = state->tkin ? (char *)state->tkin + 24 * N * off : nullptr;
         sub.tpsi0 = state->tpsi0 ? state->tpsi0 + off : nullptr;
+        sub.spawn_sep = state->spawn_sep ? state->spawn_sep + off : nullptr;
         sub.pstage = state->pstage ? (char *)state->pstage + ACAS2D_PSTAGE_BYTES * off : nullptr;   // [7][n] block of this chunk
         sub.env_id_offset = state->env_id_offset + (uint64_t)off;
         acas2d_step_aux sa = {};

@@ -74,6 +74,8 @@ struct DevParams {
     int32_t q3_trivial;     // every spawned intruder flies at exactly AIRSPEED (factor min == max == 1): Q3's term == dy
     float coll_sure_d2;     // (2*COLLISION_RADIUS - 0.05)^2: a float32 separation estimate below this IS a collision
     float dt_f;
+    float vrel_step;        // upper bound of the player-intruder relative displacement per step (spawned speeds), rounded up
+    float coll_sure;        // 2*COLLISION_RADIUS - 1e-3: a separation bound below this proves a collision
 };
 
 // forward: used by sincos_deg below

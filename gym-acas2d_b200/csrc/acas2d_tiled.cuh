@@ -46,7 +46,7 @@ struct alignas(16) PlayerStage {
     float obs[5];           // player-only observation entries
     float d_goal, phi_deg, d_dev, ep_return, minsep;
     int32_t steps_word;     // paux.steps as read (flag bits included)
-    int32_t pad_;
+    float spawn_sep;        // the game's minimum separation at its spawn (+inf: unknown)
 };
 static_assert(sizeof(PlayerStage) == ACAS2D_PSTAGE_BYTES, "PlayerStage layout");
 constexpr int kStageWords = sizeof(PlayerStage) / 16;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void player_phase(const DevParams &P, const StatePtrs
     o.ep_return = pa.ep_return;
     o.minsep = minsep ? S.min_sep[env] : INFINITY;
     o.steps_word = pa.steps;
-    o.pad_ = 0;
+    o.spawn_sep = S.spawn_sep ? S.spawn_sep[env] : INFINITY;
 }
 
 // PlayerStage <-> seven 16-byte words, through registers (no address of the struct is taken)
@@ -116,7 +116,7 @@ __device__ __forceinline__ void stage_store(Float4 *__restrict__ dst, int64_t B,
     dst[4 * B + env] = w;
     w.x = o.obs[4]; w.y = o.d_goal; w.z = o.phi_deg; w.w = o.d_dev;
     dst[5 * B + env] = w;
-    w.x = o.ep_return; w.y = o.minsep; w.z = __int_as_float(o.steps_word); w.w = 0.0f;
+    w.x = o.ep_return; w.y = o.minsep; w.z = __int_as_float(o.steps_word); w.w = o.spawn_sep;
     dst[6 * B + env] = w;
 }
 
@@ -127,7 +127,7 @@ __device__ __forceinline__ void stage_load(const Float4 *__restrict__ src, int64
     unpack_dd(w0, o.x, o.y); unpack_dd(w1, o.c, o.s); unpack_dd(w2, o.cl, o.sl); unpack_dd(w3, o.psi, o.dg2);
     o.obs[0] = w4.x; o.obs[1] = w4.y; o.obs[2] = w4.z; o.obs[3] = w4.w;
     o.obs[4] = w5.x; o.d_goal = w5.y; o.phi_deg = w5.z; o.d_dev = w5.w;
-    o.ep_return = w6.x; o.minsep = w6.y; o.steps_word = __float_as_int(w6.z); o.pad_ = 0;
+    o.ep_return = w6.x; o.minsep = w6.y; o.steps_word = __float_as_int(w6.z); o.spawn_sep = w6.w;
 }
 
 // The player pre-pass: one thread per env, result as seven 16-byte words per env, structure of arrays.
@@ -182,8 +182,22 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
     const int64_t span0 = env0 * L;
     float *otile = (float *)(tile + tile_bytes) + (int)(span0 & 3);
 
+    // 0. one env per warp (N >= 256), lean launch: is this game's collision already certain?  Its minimum separation
+    //    AT SPAWN (state->spawn_sep) plus the largest distance two aircraft can have closed in k steps bounds the
+    //    separation of its closest intruder from above; below 2 * COLLISION_RADIUS the game ends now (game.py:185-189),
+    //    respawns, and emits nothing that depends on the other intruders -- the tile is not even fetched.  With the
+    //    reference's spawn rule (intruders uniform over the region the player starts in, game.py:109-110) that is
+    //    ~99.7 % of the env-steps at N = 256 (203 -> 189 us).
+    bool certain = false;
+    if (G == 32 && !MINSEP && P.auto_reset && out.term_obs == nullptr && S.pstage && S.spawn_sep && nvalid > 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const Float4 w6 = S.pstage[6 * S.B + env0];
+        const int k0 = __float_as_int(w6.z) & kStepsMask;
+        certain = w6.w + (float)k0 * P.vrel_step < P.coll_sure;
+    }
+
     // 1. stage the traffic tile
-    if (nvalid > 0) {
+    if (nvalid > 0 && !certain) {
         if (G > 1) {                            // unpadded rows: one bulk copy of the warp's contiguous span
             if (lane == 0) {
                 mbar_init(&tile_bar[warp], 1);
@@ -225,7 +239,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         ps.x = ps.y = ps.c = ps.s = ps.cl = ps.sl = ps.psi = ps.dg2 = 0.0;
         ps.obs[0] = ps.obs[1] = ps.obs[2] = ps.obs[3] = ps.obs[4] = 0.0f;
         ps.d_goal = ps.phi_deg = ps.d_dev = ps.ep_return = 0.0f; ps.minsep = INFINITY;
-        ps.steps_word = 1; ps.pad_ = 0;
+        ps.steps_word = 1; ps.spawn_sep = INFINITY;
     }
     Tally tally;
     tally_clear(tally);
@@ -241,7 +255,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
 
         if (G > 1) {
             __syncwarp();                                                   // the barrier was initialised by lane 0
-            mbar_wait(smem_u32(&tile_bar[warp]), 0);
+            if (!certain) mbar_wait(smem_u32(&tile_bar[warp]), 0);
         } else {
             __pipeline_wait_prior(0);
             __syncwarp();
@@ -279,8 +293,8 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         // for sure": exact float64 separations from the cache, or a float32 estimate from the records with a 0.05 px
         // margin (MUFU sin / cos: < 3e-3 px off after 1000 steps).  If so the full pass is skipped; the reward's
         // intruder-0 terms are computed on their own.  Anything short of certain takes the full, exact pass.
-        bool skip = false;
-        if (G == 32 && !MINSEP && P.auto_reset && out.term_obs == nullptr) {
+        bool skip = certain;
+        if (G == 32 && !MINSEP && P.auto_reset && out.term_obs == nullptr && !certain) {
             bool hit = false;
             int jp = j0;
             if (KIN && fast) {
@@ -311,7 +325,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         if (skip) {
             coll = true;
             if (lane == 0) {                                                // j0 == 0 for lane 0: intruder 0 (Q7)
-                if (KIN && fast) e0 = encounter(P, p, intruder_from_kin(((const TrafficKin *)tile)[0], kd));
+                if (KIN && fast && !certain) e0 = encounter(P, p, intruder_from_kin(((const TrafficKin *)tile)[0], kd));
                 else e0 = encounter(P, p, intruder_at(P, traffic_load(S, env * N, residual), kd));
             }
         } else if (KIN && fast) {
@@ -443,6 +457,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
 #pragma unroll
                     for (int q = 0; q < 5; ++q) rrow[q] = v1.obs[q];
                 }
+                if (lane == 0 && S.spawn_sep) S.spawn_sep[renv] = ms;
                 if (e == row) { p.x = rp.x; p.y = rp.y; p.psi = rp.psi; minsep = ms; steps_out = 1 | spawn_bits(P, S); ret = 0.0f; }
             }
         }

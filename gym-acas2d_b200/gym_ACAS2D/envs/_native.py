@@ -68,7 +68,8 @@ class State(ctypes.Structure):
                 ("episode_idx", ctypes.c_void_p), ("min_sep", ctypes.c_void_p),
                 ("stats", ctypes.c_void_p),
                 ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_uint64),
-                ("tkin", ctypes.c_void_p), ("tpsi0", ctypes.c_void_p), ("pstage", ctypes.c_void_p)]
+                ("tkin", ctypes.c_void_p), ("tpsi0", ctypes.c_void_p), ("pstage", ctypes.c_void_p),
+                ("spawn_sep", ctypes.c_void_p)]
 
 
 class PpoConfig(ctypes.Structure):

@@ -75,6 +75,8 @@ class BatchedACAS2D:
             self.tpsi0 = torch.zeros(B, dtype=f32, device=dev) if N == 1 else None     # compact intruder-0 headings
             # per-step scratch of the player pre-pass (N > 1): 7 x 16 B per env, structure of arrays
             self.pstage = torch.zeros(_native.PSTAGE_BYTES // 16, B, 4, dtype=f32, device=dev) if N > 1 else None
+            # minimum separation of each game at its spawn (N > 1): proves first-step collisions without reading intruders
+            self.spawn_sep = torch.full((B,), float("inf"), dtype=f32, device=dev) if N > 1 else None
             self.episode_idx = torch.zeros(B, dtype=torch.int32, device=dev)
             self.min_sep = torch.zeros(B, dtype=f32, device=dev) if track_min_sep else None
             self.stats = torch.zeros(_native.STAT_SLOTS, _native.STAT_FIELDS, dtype=torch.int64, device=dev)
@@ -91,7 +93,8 @@ class BatchedACAS2D:
             stats=self.stats.data_ptr(), seed=self.seed, env_id_offset=self.env_id_offset,
             tkin=self.tkin.data_ptr() if self.tkin is not None else None,
             tpsi0=self.tpsi0.data_ptr() if self.tpsi0 is not None else None,
-            pstage=self.pstage.data_ptr() if self.pstage is not None else None)
+            pstage=self.pstage.data_ptr() if self.pstage is not None else None,
+            spawn_sep=self.spawn_sep.data_ptr() if self.spawn_sep is not None else None)
         self._aux_full = StepAux(flags=self.flags.data_ptr(), outcome=self.outcome.data_ptr(),
                                  term_obs=self.term_obs.data_ptr(), ep_return=self.ep_return.data_ptr(),
                                  ep_length=self.ep_length.data_ptr())
@@ -479,7 +482,7 @@ class BatchedACAS2D:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Checkpoint of the env batch (the reference never saves env state)."""
         d = {k: getattr(self, k).detach().clone() for k in self._STATE_TENSORS}
-        for k in ("min_sep", "tkin", "tpsi0"):
+        for k in ("min_sep", "tkin", "tpsi0", "spawn_sep"):
             if getattr(self, k) is not None:
                 d[k] = getattr(self, k).clone()
         d["meta"] = torch.tensor([self.num_envs, self.n_traffic, self.seed, self.env_id_offset], dtype=torch.int64)
@@ -495,7 +498,7 @@ class BatchedACAS2D:
             self._state.seed, self._state.env_id_offset = self.seed, self.env_id_offset
         for k in self._STATE_TENSORS:
             getattr(self, k).copy_(d[k])
-        for k in ("min_sep", "tkin", "tpsi0"):
+        for k in ("min_sep", "tkin", "tpsi0", "spawn_sep"):
             if getattr(self, k) is not None:
                 if k not in d:
                     if k == "min_sep":

@@ -142,6 +142,10 @@ typedef struct acas2d_state {
     void     *pstage;         /* optional scratch (N > 1), ACAS2D_PSTAGE_BYTES per env: with it the float64 player update of
                                  a step runs as its own one-thread-per-env launch and the tiled kernel's lanes read its
                                  result, instead of every lane of an env's group redoing it; contents are per-step */
+    float    *spawn_sep;      /* optional (N > 1), float[B]: the game's minimum player-intruder separation AT ITS SPAWN (+inf after
+                                 an injection).  Aircraft move at bounded speed, so spawn_sep + k * (largest relative displacement per
+                                 step) < 2 * COLLISION_RADIUS proves a collision at step k without looking at a single intruder:
+                                 with N >= 256 the reference's spawn rule ends nearly every game that way on its first step */
 } acas2d_state;
 
 /* Optional per-step outputs (any pointer may be NULL). */
