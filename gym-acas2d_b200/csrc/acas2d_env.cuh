@@ -130,6 +130,12 @@ inline DevParams make_dev_params(const acas2d_params &p)
     const double sure = 2.0 * p.collision_radius - 0.05;
     d.coll_sure_d2 = sure > 0.0 ? (float)(sure * sure) : 0.0f;
     d.dt_f = (float)dt;
+    {   // the new game's player-only observation entries (see reset_view)
+        Player p0;
+        p0.x = p.player_x0; p0.y = p.player_y0; p0.psi = 0.0; p0.c = 1.0; p0.s = 0.0; p0.cl = 1.0; p0.sl = 0.0;
+        const PlayerView v0 = player_view(d, p0, 1);
+        d.reset_obs0 = v0.obs[0]; d.reset_obs2 = v0.obs[2]; d.reset_obs3 = v0.obs[3]; d.reset_obs4 = v0.obs[4];
+    }
     d.vrel_step = (float)(p.airspeed * dt * (1.0 + p.airspeed_factor_max) * (1.0 + 1e-6));
     d.coll_sure = (float)(2.0 * p.collision_radius - 1e-3);
     return d;
@@ -361,7 +367,7 @@ ACAS_HD void respawn_env1(const DevParams &P, const StatePtrs &S, Env1 &e, int64
     player_set_heading_straight(p, sp.player_psi);                          // a_lat = 0 in a new game
     e.tr = spawn_traffic(P, S.seed, gid, episode, 0, sp);
     const Intruder t = intruder_at(P, e.tr, 0.0);
-    const PlayerView v1 = player_view(P, p, 1);
+    const PlayerView v1 = reset_view(P, p.psi);
     const Encounter e1 = encounter(P, p, t);
     if (EMIT) store_obs8(out.obs + 8 * i, v1, e1, P);
     e.px = p.x; e.py = p.y; e.psi = p.psi; e.steps = 1; e.ret = 0.0f;
@@ -553,7 +559,7 @@ ACAS_HD void step_env_loop(const DevParams &P, const StatePtrs &S, int64_t i, fl
             const Spawn0 sp = spawn_slot0(P, S.seed, gid, episode);
             p.x = P.player_x0; p.y = P.player_y0;
             player_set_heading_straight(p, sp.player_psi);
-            const PlayerView v1 = player_view(P, p, 1);
+            const PlayerView v1 = reset_view(P, p.psi);
 #pragma unroll
             for (int q = 0; q < 5; ++q) row[q] = v1.obs[q];
             minsep = INFINITY;
@@ -678,7 +684,7 @@ ACAS_HD void reset_env(const DevParams &P, const StatePtrs &S, int64_t i, float 
     Player p;
     p.x = P.player_x0; p.y = P.player_y0;
     player_set_heading_straight(p, sp.player_psi);
-    const PlayerView v = player_view(P, p, 1);
+    const PlayerView v = reset_view(P, p.psi);
     float *row = obs ? obs + (int64_t)L * i : nullptr;
     if (row) for (int q = 0; q < 5; ++q) row[q] = v.obs[q];
     float minsep = INFINITY;

@@ -74,6 +74,7 @@ struct DevParams {
     int32_t q3_trivial;     // every spawned intruder flies at exactly AIRSPEED (factor min == max == 1): Q3's term == dy
     float coll_sure_d2;     // (2*COLLISION_RADIUS - 0.05)^2: a float32 separation estimate below this IS a collision
     float dt_f;
+    float reset_obs0, reset_obs2, reset_obs3, reset_obs4;   // player-only observation entries of a NEW game (all but the heading)
     float vrel_step;        // upper bound of the player-intruder relative displacement per step (spawned speeds), rounded up
     float coll_sure;        // 2*COLLISION_RADIUS - 1e-3: a separation bound below this proves a collision
 };
@@ -400,6 +401,18 @@ ACAS_HD PlayerView player_view(const DevParams &P, const Player &p, int32_t step
     v.obs[2] = gyf * P.inv_d_dev_max_f;
     v.obs[3] = v.d_goal * P.inv_d_goal_max;
     v.obs[4] = phi_turns;
+    return v;
+}
+
+// Player-only observation entries of a freshly spawned game (game.py:199-203 at steps == 1): the player starts at a
+// fixed point (game.py:85-86), so everything but obs[1] = psi / 360 is a constant of the parameter set
+// (make_dev_params evaluates player_view there once) -- a respawn does not redo the goal distance / bearing math.
+ACAS_HD PlayerView reset_view(const DevParams &P, double psi)
+{
+    PlayerView v;
+    v.obs[0] = P.reset_obs0; v.obs[1] = (float)(psi * P.inv_360); v.obs[2] = P.reset_obs2;
+    v.obs[3] = P.reset_obs3; v.obs[4] = P.reset_obs4;
+    v.dg2 = 0.0; v.d_goal = 0.0f; v.phi_deg = 0.0f; v.d_dev = 0.0f;     // not used by the reset observation
     return v;
 }
 

@@ -453,7 +453,7 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ms = fminf(ms, __shfl_xor_sync(kFull, ms, o));
                 if (lane == 0) {
-                    const PlayerView v1 = player_view(P, rp, 1);
+                    const PlayerView v1 = reset_view(P, rp.psi);
 #pragma unroll
                     for (int q = 0; q < 5; ++q) rrow[q] = v1.obs[q];
                 }
