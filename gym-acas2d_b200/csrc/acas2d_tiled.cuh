@@ -368,10 +368,12 @@ step_tiled_kernel(const DevParams P, const StatePtrs S, const float *__restrict_
         }
 
         // 4. reductions over the G lanes of the env
+        if (!(G == 32 && skip)) {                                           // (a settled collision needs no vote)
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            coll |= (bool)__shfl_xor_sync(kFull, (int)coll, o);
-            if (MINSEP) minsep = fminf(minsep, __shfl_xor_sync(kFull, minsep, o));
+            for (int o = G / 2; o > 0; o >>= 1) {
+                coll |= (bool)__shfl_xor_sync(kFull, (int)coll, o);
+                if (MINSEP) minsep = fminf(minsep, __shfl_xor_sync(kFull, minsep, o));
+            }
         }
 
         // 5. reward, flags, bookkeeping (lane `sub == 0` owns intruder 0, Q7)
