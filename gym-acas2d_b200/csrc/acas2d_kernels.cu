@@ -72,7 +72,7 @@ int finish_launch(int kernels = 1)
 // Tuning knobs for experiments (read once): ACAS2D_N1_OCC = 1..4 resident CTAs/SM for the N == 1 kernel
 // (fewer concurrent DRAM streams win: 2 CTAs x 2 stages = 87.7 us, 3 x 2 = 91.3, 4 x 2 = 93.0, 1 x 2 = 118),
 // ACAS2D_FORCE_LOOP = 1 routes N > 1 to the simple per-thread kernel the tiled one is checked against.
-struct Tuning { int n1_occupancy; bool force_loop; int n1_tma; int n1_stages; };
+struct Tuning { int n1_occupancy; bool force_loop; int n1_tma; int n1_stages; int n1_pdl; };
 Tuning &tuning()
 {
     static Tuning t = [] {
@@ -85,6 +85,8 @@ Tuning &tuning()
         x.n1_tma = t ? std::atoi(t) : 1;
         const char *g = std::getenv("ACAS2D_N1_STAGES");
         x.n1_stages = g ? std::atoi(g) : 2;                       // ring depth barely matters once loads are off the warps
+        const char *d = std::getenv("ACAS2D_N1_PDL");
+        x.n1_pdl = d ? std::atoi(d) : 1;                           // programmatic dependent launch of consecutive steps
         return x;
     }();
     return t;
@@ -172,6 +174,12 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, bar, pol);
     };
 
+    // Programmatic dependent launch: consecutive steps are launched so that step k+1's CTAs may take an SM slot as
+    // soon as one of step k's CTAs has left it (the launch gap between two dependent kernels is otherwise ~2.4 us
+    // of an 80 us step); everything up to here touched no global memory.  Step k's state is complete only once its
+    // whole grid has finished: wait for that before the first tile is fetched.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -281,11 +289,16 @@ int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, 
     long long grid = (long long)sms * OCC;
     const long long tiles = full_tiles + ((S.B % kTileEnvs) ? 1 : 0);
     if (grid > tiles) grid = tiles;
-    if (compact)
-        step_n1_tma_kernel<STAGES, OCC, TILE, true><<<(unsigned)grid, TILE, STAGES * stage_bytes + 64, st>>>(P, S, actions, out, full_tiles);
-    else
-        step_n1_tma_kernel<STAGES, OCC, TILE, false><<<(unsigned)grid, TILE, STAGES * stage_bytes + 64, st>>>(P, S, actions, out, full_tiles);
-    return 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TILE); lc.dynamicSmemBytes = STAGES * stage_bytes + 64; lc.stream = st;
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = tuning().n1_pdl ? 1 : 0;
+    lc.attrs = &pdl; lc.numAttrs = 1;
+    const long long ft = full_tiles;
+    cudaError_t err = compact ? cudaLaunchKernelEx(&lc, step_n1_tma_kernel<STAGES, OCC, TILE, true>, P, S, actions, out, ft)
+                              : cudaLaunchKernelEx(&lc, step_n1_tma_kernel<STAGES, OCC, TILE, false>, P, S, actions, out, ft);
+    return err == cudaSuccess ? 0 : (int)err;
 }
 
 // ---------------------------------------------------------------- policy + env step (N_TRAFFIC == 1)
