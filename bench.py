@@ -285,9 +285,12 @@ def age_batch(env, steps: int) -> int:
     # all games start together at reset, and a quarter of the random-action games run into the 1000-step timeout: left
     # alone they keep ending in WAVES 1000 steps apart.  Stagger the step counters once (the games then time out
     # at different moments) and let the ageing steps mix the rest.
-    words = env.paux.view(torch.int32).view(env.num_envs, 4)[:, 2]                   # paux.steps (flag bits above bit 27)
-    gid = torch.arange(env.num_envs, device=env.device, dtype=torch.int64) + env.env_id_offset
-    words.add_(((gid * 7919) % 997).to(torch.int32))
+    # (Only where the ageing is long enough to play these first, displaced games out: N_TRAFFIC == 1.  With more
+    # intruders episodes last a few steps and end by collision -- there are no timeout waves to break up.)
+    if env.n_traffic == 1 and steps >= 1500:
+        words = env.paux.view(torch.int32).view(env.num_envs, 4)[:, 2]               # paux.steps (flag bits above bit 27)
+        gid = torch.arange(env.num_envs, device=env.device, dtype=torch.int64) + env.env_id_offset
+        words.add_(((gid * 7919) % 997).to(torch.int32))
     if env.n_traffic == 1:
         env.rollout_random(steps, action_seed=77, step0=0)
         env.observe()                                   # the obs buffer of the aged state (a_lat taken as 0)
