@@ -22,8 +22,9 @@ for s in secs[1:]:
     dem = subprocess.run(["c++filt", mangled], capture_output=True, text=True).stdout.strip()
     def norm(x):
         x = re.sub(r"\((int|bool)\)", "", x).replace(" ", "").replace("void", "")
+        x = x.replace("<unnamed>::", "").replace("(anonymousnamespace)::", "").replace("acas2d::", "")
         x = x.replace("false", "0").replace("true", "1")
-        return x.split("(acas2d::DevParams")[0].split("(DevParams")[0]
+        return x.split("(DevParams")[0]
     if norm(dem) == norm(kname):
         best = s
         break
