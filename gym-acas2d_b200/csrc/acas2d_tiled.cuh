@@ -1,7 +1,10 @@
 // acas2d_tiled.cuh -- N_TRAFFIC > 1: the shared-memory tiled step kernel.
 //
 // G lanes cooperate on one env (G = 1, 2, ..., 32; G divides N), so a warp owns E = 32/G consecutive envs
-// and every lane handles N/G intruders; a CTA is four warps = 4E envs.
+// and every lane handles N/G intruders; a CTA is ONE warp (four when G == 32, see TiledShape).
+//   0. one env per warp (N >= 256), lean launch: the game's minimum separation at its spawn (state->spawn_sep)
+//      bounds its closest intruder's separation k steps later; when that proves a collision the tile is not
+//      fetched and the per-intruder pass is skipped (a respawning env emits none of its results);
 //   1. each warp stages its traffic tile -- contiguous in HBM -- into shared memory: ONE TMA bulk copy per warp
 //      (cp.async.bulk + the warp's mbarrier) when rows are unpadded (G > 1), cp.async pieces otherwise.  KIN: the
 //      tile is the 24-byte kinematic cache {x0, y0 float; dx, dy double} (acas2d_b200.h "tkin"), else the
@@ -10,18 +13,20 @@
 //      player update (aircraft.py:16-26), the look-ahead heading (kinematics.py:57-60) and the player-only
 //      observation terms run as their own one-thread-per-env launch (player_phase_kernel: a ~400-instruction
 //      dependent chain at full lane occupancy instead of G-fold redundantly inside every group -- and off the
-//      tiled kernel's critical path); the lanes read the result while their tile copy flies.  G == 1, or no
-//      scratch: each lane does it in registers.
+//      tiled kernel's critical path, which is launched as its programmatic dependent); the lanes read the result
+//      while their tile copy flies.  G == 1, or no scratch: each lane does it in registers.
 //   3. each lane walks its intruders.  KIN: position = origin + k * cached displacement -- no sin / cos, no
-//      float32 -> float64 conversion of a heading; 21 float64 operations, 3 MUFU and 4 conversions per intruder
-//      (the loop is bound by the 16-lane conversion / MUFU pipe, see acas2d_math.cuh).  Collision / minimum
-//      separation partials stay in registers, the three observation entries go to the warp's observation tile;
+//      float32 -> float64 conversion of a heading; 21 float64 operations, 3 MUFU and 4 conversions per intruder,
+//      two intruders in flight (the round-1 loop was bound by the 16-lane conversion / MUFU pipe, see
+//      acas2d_math.cuh).  Collision / minimum separation partials stay in registers, the three observation
+//      entries go to the warp's observation tile.  One env per warp, lean launch: a cheap first pass (exact
+//      cached separations, or a float32 estimate with a 0.05 px margin) may settle the collision and skip this;
 //   4. any-collision and min-separation are reduced over the G lanes with xor shuffles;
 //   5. lane 0 of each group finishes reward / flags / episode bookkeeping;
 //   6. finished envs respawn cooperatively: all 32 lanes take the intruders of each respawning env in turn
-//      (one Philox block per intruder), write its records and its reset observation;
-//   7. the observation tile is written back as one contiguous span: one TMA bulk store per warp when the span
-//      is 16-byte aligned, 32-bit streaming stores otherwise.
+//      (one Philox block per intruder, records float32 end to end), write its records and its reset observation;
+//   7. the observation tile -- laid out with the HBM span's own phase within a 16-byte word -- is written back as
+//      one contiguous span: one TMA bulk store per warp for the aligned body, <= 3 scalar floats at either end.
 #pragma once
 
 #include <cuda_pipeline.h>
