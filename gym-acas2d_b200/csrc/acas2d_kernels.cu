@@ -4,18 +4,26 @@
 // Kernels
 //   step_n1_tma_kernel    N_TRAFFIC == 1 (the reference default), persistent: 256-env input tiles
 //                         arrive through a TMA bulk-copy ring (cp.async.bulk + mbarrier), threads
-//                         compute out of shared memory and stream results with 128-bit stores.
+//                         compute out of shared memory and stream results with 128-bit stores; compact
+//                         4-byte intruder record, respawns deferred to a per-CTA queue, consecutive steps
+//                         chained by programmatic dependent launch.
 //   step_n1_kernel        same step, one thread per env with plain 128-bit loads (used when the
 //                         per-episode minimum separation is tracked; bit-identical results).
-//   step_tiled_kernel     N_TRAFFIC > 1: G lanes per env (G = 1..32), the warp's traffic
-//                         tile staged in shared memory with cp.async, min-separation /
-//                         any-collision reduced with warp shuffles, observation rows
-//                         assembled in shared memory and written back coalesced.
-//   rollout_n1_kernel     K fused steps with in-kernel Philox actions (synthetic benchmark).
+//   step_tiled_kernel     (acas2d_tiled.cuh) N_TRAFFIC > 1: G lanes per env (G = 1..32), the warp's traffic
+//                         tile -- 24-byte kinematic cache or 16-byte records -- staged in shared memory by one
+//                         TMA bulk copy per warp, min-separation / any-collision reduced with warp shuffles,
+//                         observation rows assembled in shared memory and written back by one TMA bulk store.
+//   player_phase_kernel   (acas2d_tiled.cuh) the float64 player update of a step, one thread per env, for the
+//                         tiled kernel's lanes to read.
+//   step_loop_kernel      N_TRAFFIC > 1, one thread per env: the simple form the tiled kernel is checked against.
+//   rollout_n1_kernel     K fused steps with in-kernel Philox actions (synthetic benchmark, ageing).
+//   step_k_n1_kernel      K open-loop steps per launch with every step's outputs.
 //   policy_step_n1_kernel / policy_step_n1_tc_kernel (acas2d_policy*.cuh)
-//                         the reference agent's actor MLP fused with the env step: float32 on the
-//                         CUDA cores, or tcgen05 TF32 MMAs with TMEM accumulators.
-//   reset / observe / inject / extract / random_actions  small utility kernels.
+//                         the reference agent's actor MLP fused with the env step: float32 on the CUDA cores,
+//                         or tcgen05 TF32 MMAs with TMEM accumulators.
+//   ppo_* kernels         (acas2d_ppo.cuh) critic forward, GAE, minibatch gradient, fused update.
+//   trace_kernel          per-step episode records into ring buffers (acas2d_trace_step).
+//   reset / observe / inject / extract / render / random_actions  small utility kernels.
 //
 // There is no CPU fallback in this file: every entry point launches on the device.
 #include <cuda_runtime.h>
