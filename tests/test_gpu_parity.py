@@ -158,7 +158,7 @@ def test_traffic_sweep_vs_oracle(cuda, n, B, T):
     assert np.abs(ex["traffic"][:, :, :2] - st["traffic"][:, :, :2]).max() < parity.TOL_POS
 
 
-@pytest.mark.parametrize("n,T", [(8, 60), (64, 40), (256, 24)])
+@pytest.mark.parametrize("n,T", [(8, 60), (16, 40), (32, 40), (64, 40), (128, 24), (256, 24)])
 def test_config4_parity_at_stated_batch(cuda, n, T):
     """BASELINE config 4 AT ITS STATED BATCH: 65 536 envs, N_TRAFFIC = 8 / 64 / 256, auto-reset, random actions.
     Eight 64-env windows spread over the batch (first / last warps and CTAs, odd offsets) are stepped by the
@@ -466,6 +466,30 @@ def test_host_buffer_step_equals_device_step(cuda):
         o1, r1, d1 = a.step(torch.from_numpy(act).cuda())
         o2, r2, d2 = b.step_host(act)
         assert np.array_equal(npy(o1), o2) and np.array_equal(npy(r1), r2) and np.array_equal(npy(d1), d2)
+
+
+@pytest.mark.parametrize("n,B", [(1, 600_000 + 77), (16, 600_000), (256, 530_000)])
+def test_chunked_host_step_equals_device_step(cuda, n, B):
+    """Large batches take acas2d_step_host's chunk pipeline (256 Ki-env chunks rotating over three streams, each chunk a
+    sub-batch view of every state array -- records, kinematic cache, compact headings, pre-pass scratch, spawn
+    separations -- with its own global env id offset): bit-identical to the one-launch device step, state included."""
+    a = make(B, n, seed=12, auto_reset=True); b = make(B, n, seed=12, auto_reset=True)
+    assert B > a.PACKED_HOST_LIMIT and B >= 2 * 262144
+    a.reset(); b.reset()
+    if n == 1:                                           # age the single-intruder games: episodes end on every step
+        a.rollout_random(1200, action_seed=1); b.rollout_random(1200, action_seed=1)
+        a.clear_stats(); b.clear_stats()
+    for t in range(6 if n == 256 else 12):
+        act = a.random_actions(t, action_seed=4)
+        o1, r1, d1 = a.step(act)
+        o2, r2, d2 = b.step_host(act.cpu().numpy())
+        assert np.array_equal(npy(o1).view(np.int32), o2.view(np.int32)), t
+        assert np.array_equal(npy(r1), r2) and np.array_equal(npy(d1), d2), t
+    assert torch.equal(a.ppos, b.ppos) and torch.equal(a.paux, b.paux) and torch.equal(a.thot, b.thot)
+    assert torch.equal(a.episode_idx, b.episode_idx) and torch.equal(a.episode_counters(), b.episode_counters())
+    if n > 1:
+        assert torch.equal(a.spawn_sep, b.spawn_sep)
+    assert int(a.episode_counters()[0]) > 1000
 
 
 def test_fused_rollout_equals_stepwise_and_graph(cuda):
