@@ -809,6 +809,13 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state, con
     return (int)cudaStreamSynchronize(st);
 }
 
+int acas2d_step_mapped(const acas2d_params *params, const acas2d_state *state, const float *actions, float *obs,
+                       float *reward, uint8_t *done, const acas2d_step_aux *aux, void *stream)
+{
+    if (int e = acas2d_step(params, state, actions, obs, reward, done, aux, stream)) return e;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
 int acas2d_step_host_packed(const acas2d_params *params, const acas2d_state *state, const float *h_actions,
                             float *d_actions, float *obs, float *reward, uint8_t *done, const acas2d_step_aux *aux,
                             const void *d_packed, void *h_packed, int64_t packed_bytes, void *stream)

@@ -44,7 +44,7 @@ EXPORTS = ("acas2d_abi_version", "acas2d_params_default", "acas2d_reset", "acas2
            "acas2d_inject_state", "acas2d_extract_state", "acas2d_rollout_random", "acas2d_random_actions",
            "acas2d_launch_count", "acas2d_set_tuning", "acas2d_set_n1_kernel", "acas2d_policy_step", "acas2d_observe", "acas2d_render",
            "acas2d_ppo_values", "acas2d_ppo_gae", "acas2d_ppo_grad", "acas2d_ppo_adam", "acas2d_ppo_step",
-           "acas2d_ppo_prepare", "acas2d_policy_step_dyn", "acas2d_step_k", "acas2d_set_tiled_tuning", "acas2d_step_host_packed", "acas2d_trace_step")
+           "acas2d_ppo_prepare", "acas2d_policy_step_dyn", "acas2d_step_k", "acas2d_set_tiled_tuning", "acas2d_step_host_packed", "acas2d_trace_step", "acas2d_step_mapped")
 
 ERRORS = {-1: "required pointer is NULL", -2: "unsupported n_traffic", -3: "bad size", -4: "no CUDA device"}
 
@@ -124,6 +124,7 @@ def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.acas2d_params_default.argtypes = [PP, ctypes.c_int32]
     lib.acas2d_reset.argtypes = [PP, SP, vp, vp, vp]
     lib.acas2d_step.argtypes = [PP, SP, vp, vp, vp, vp, AP, vp]
+    lib.acas2d_step_mapped.argtypes = [PP, SP, vp, vp, vp, vp, AP, vp]
     lib.acas2d_step_k.argtypes = [PP, SP, ctypes.c_int32, vp, vp, vp, vp, AP, vp]
     lib.acas2d_step_host.argtypes = [PP, SP, vp, vp, vp, vp, vp, vp, vp, vp, AP, vp]
     lib.acas2d_step_host_packed.argtypes = [PP, SP, vp, vp, vp, vp, vp, AP, vp, vp, ctypes.c_int64, vp]

@@ -51,7 +51,7 @@ class BatchedACAS2D:
 
     def __init__(self, num_envs: int, n_traffic: Optional[int] = None, device="cuda", seed: Optional[int] = None,
                  env_id_offset: int = 0, auto_reset: bool = True, track_min_sep: bool = False,
-                 settings=None, **setting_overrides):
+                 settings=None, host_zero_copy: bool = False, **setting_overrides):
         self.lib = _native.load()
         self.device = _require_cuda(device)
         self.params: Params = _native.params_from_settings(settings, n_traffic, auto_reset, **setting_overrides)
@@ -101,6 +101,11 @@ class BatchedACAS2D:
         self._aux_lean = StepAux(flags=None, outcome=self.outcome.data_ptr(), term_obs=None,
                                  ep_return=self.ep_return.data_ptr(), ep_length=self.ep_length.data_ptr())
         self._host = None          # pinned staging buffers of step_host
+        # tiny batches (the single-env gym surface): step_host lets the kernel read the action from and write its outputs
+        # straight to the pinned (device-mapped) host block -- one launch + one sync, no copies.  The device-side
+        # output buffers (obs, reward, ...) are then NOT updated by step_host.
+        self._zero_copy = bool(host_zero_copy)
+        self._aux_host = None
         self._trace = None         # on-device episode records (enable_trace)
         self._actions_dev = torch.zeros(B, dtype=f32, device=dev)
         self.launches = 0          # kernels launched through this object
@@ -259,6 +264,26 @@ class BatchedACAS2D:
             a_ptr = actions.data_ptr()                      # caller-owned pinned memory: no staging copy
         elif actions is not None:
             np.copyto(hb["actions"], np.asarray(actions, dtype=np.float32).reshape(-1))
+        if self._zero_copy and self._trace is None:
+            if self._aux_host is None:
+                self._aux_host = StepAux(flags=h["flags"].data_ptr(), outcome=h["outcome"].data_ptr(),
+                                         term_obs=h["term_obs"].data_ptr(), ep_return=h["ep_return"].data_ptr(),
+                                         ep_length=h["ep_length"].data_ptr())
+                self._mapped_args = (self._p(), self._s(), None, h["obs"].data_ptr(), h["reward"].data_ptr(),
+                                     h["done_u8"].data_ptr(), ctypes.byref(self._aux_host))
+                self._mapped_out = (hb["obs"], hb["reward"], hb["done"].view(np.bool_))
+                # the stream current at the first call serves every later one: looking it up costs more than the launch
+                self._mapped_stream = self._stream()
+            m = self._mapped_args
+            if torch.cuda.current_device() != self.device.index:
+                with torch.cuda.device(self.device):
+                    rc = self.lib.acas2d_step_mapped(m[0], m[1], a_ptr, m[3], m[4], m[5], m[6], self._mapped_stream)
+            else:
+                rc = self.lib.acas2d_step_mapped(m[0], m[1], a_ptr, m[3], m[4], m[5], m[6], self._mapped_stream)
+            if rc:
+                _native.check(rc, "acas2d_step_mapped")
+            self.launches += 1
+            return self._mapped_out
         with torch.cuda.device(self.device):
             if self._trace is not None:                     # the trace kernel reads the actions on the device
                 src = actions if a_ptr != h["actions"].data_ptr() else h["actions"]

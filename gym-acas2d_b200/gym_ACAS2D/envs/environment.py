@@ -32,7 +32,7 @@ class ACAS2DEnv(_EnvBase):
 
     def __init__(self, n_traffic=None, device="cuda", seed=None, env_id=0, verbose=False, settings=None):
         self._core = BatchedACAS2D(1, n_traffic=n_traffic, device=device, seed=seed, env_id_offset=env_id,
-                                   auto_reset=False, settings=settings)
+                                   auto_reset=False, settings=settings, host_zero_copy=True)
         self._verbose = verbose
         self._episode = 0
         n = self._core.n_traffic

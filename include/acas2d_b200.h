@@ -187,6 +187,12 @@ int acas2d_step_host(const acas2d_params *params, const acas2d_state *state,
                      float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
                      const acas2d_step_aux *aux, void *stream);
 
+/* acas2d_step on buffers the DEVICE can address directly (pinned, mapped host memory under unified addressing), then
+ * one stream synchronisation: the kernel reads the actions from and writes every output straight to host memory --
+ * one launch, no copy.  For tiny batches (the single-env gym surface, ACAS2DEnv.step: environment.py:29-42). */
+int acas2d_step_mapped(const acas2d_params *params, const acas2d_state *state, const float *actions, float *obs,
+                       float *reward, uint8_t *done, const acas2d_step_aux *aux, void *stream);
+
 /* Host-buffer step for small (latency-bound) batches: the caller keeps obs / reward / done and every aux array
  * inside ONE device block [d_packed, d_packed + packed_bytes); after the step the whole block goes to the pinned
  * host block h_packed with a single copy (terminal rows and finished-episode records included), then the stream
