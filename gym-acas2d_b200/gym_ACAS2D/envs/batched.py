@@ -104,7 +104,9 @@ class BatchedACAS2D:
         # tiny batches (the single-env gym surface): step_host lets the kernel read the action from and write its outputs
         # straight to the pinned (device-mapped) host block -- one launch + one sync, no copies.  The device-side
         # output buffers (obs, reward, ...) are then NOT updated by step_host.
-        self._zero_copy = bool(host_zero_copy)
+        # (N == 1 and fewer envs than one 256-env tile only: those launches touch the host block with plain loads / stores;
+        #  the bulk-copy engines are kept away from mapped host memory)
+        self._zero_copy = bool(host_zero_copy) and N == 1 and B < 256
         self._aux_host = None
         self._trace = None         # on-device episode records (enable_trace)
         self._actions_dev = torch.zeros(B, dtype=f32, device=dev)
