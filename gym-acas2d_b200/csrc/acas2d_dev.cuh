@@ -77,6 +77,13 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy()
     return pol;
 }
 
+__device__ __forceinline__ uint64_t l2_evict_last_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gmem_src, unsigned bytes, uint32_t bar,
                                             uint64_t policy = 0)

@@ -470,6 +470,24 @@ ACAS_HD void load_env1(const StatePtrs &S, int64_t i, Env1 &e, bool minsep)
     e.respawned = false;
 }
 
+// store_env1 with an L2 cache-hint policy on the two player records (device only): the persistent N == 1 kernel keeps
+// a slice of the player state L2-resident across launches (createpolicy evict_last), the rest streams (evict_first).
+#if defined(__CUDACC__)
+__device__ __forceinline__ void store_env1_hinted(const StatePtrs &S, int64_t i, const Env1 &e, uint64_t policy)
+{
+    Vec2d pp; pp.x = e.px; pp.y = e.py;
+    PlayerAux pa; pa.psi = e.psi; pa.steps = e.steps | e.bits; pa.ep_return = e.ret;
+    Float4 a, b;
+    a.x = __int_as_float(__double2loint(pp.x)); a.y = __int_as_float(__double2hiint(pp.x));
+    a.z = __int_as_float(__double2loint(pp.y)); a.w = __int_as_float(__double2hiint(pp.y));
+    b.x = __int_as_float(__double2loint(pa.psi)); b.y = __int_as_float(__double2hiint(pa.psi));
+    b.z = __int_as_float(pa.steps); b.w = pa.ep_return;
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(S.ppos + i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "l"(policy) : "memory");
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(S.paux + i), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(policy) : "memory");
+    if (e.respawned) traffic_store(S, i, e.tr, false);
+}
+#endif
+
 ACAS_HD void store_env1(const StatePtrs &S, int64_t i, const Env1 &e, bool minsep)
 {
     Vec2d pp; pp.x = e.px; pp.y = e.py;

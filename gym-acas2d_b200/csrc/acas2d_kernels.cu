@@ -80,7 +80,7 @@ int finish_launch(int kernels = 1)
 // Tuning knobs for experiments (read once): ACAS2D_N1_OCC = 1..4 resident CTAs/SM for the N == 1 kernel
 // (fewer concurrent DRAM streams win: 2 CTAs x 2 stages = 87.7 us, 3 x 2 = 91.3, 4 x 2 = 93.0, 1 x 2 = 118),
 // ACAS2D_FORCE_LOOP = 1 routes N > 1 to the simple per-thread kernel the tiled one is checked against.
-struct Tuning { int n1_occupancy; bool force_loop; int n1_tma; int n1_stages; int n1_pdl; };
+struct Tuning { int n1_occupancy; bool force_loop; int n1_tma; int n1_stages; int n1_pdl; int n1_keep_mb; };
 Tuning &tuning()
 {
     static Tuning t = [] {
@@ -95,6 +95,9 @@ Tuning &tuning()
         x.n1_stages = g ? std::atoi(g) : 2;                       // ring depth barely matters once loads are off the warps
         const char *d = std::getenv("ACAS2D_N1_PDL");
         x.n1_pdl = d ? std::atoi(d) : 1;                           // programmatic dependent launch of consecutive steps
+        const char *kmb = std::getenv("ACAS2D_N1_KEEP_MB");
+        x.n1_keep_mb = kmb ? std::atoi(kmb) : 32;                  // MB of player state kept L2-resident across launches
+                                                                   // (measured: 0 -> 79.1, 16 -> 77.7, 27 -> 77.4, 40 -> 77.3, 60 -> 77.9 us)
         return x;
     }();
     return t;
@@ -143,7 +146,7 @@ constexpr int kRespawnQueue = 256;
 template <int STAGES, int OCC, int TILE, bool COMPACT>
 __global__ void __launch_bounds__(TILE, OCC)
 step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict__ actions, const Sinks out,
-                   const long long full_tiles)
+                   const long long full_tiles, const long long keep_tiles)
 {
     constexpr int kTileEnvs = TILE, kTraffic = COMPACT ? 4 : 16, kStageBytes = TILE * (16 + 16 + kTraffic + 4);
     constexpr int kOffPaux = TILE * 16, kOffThot = TILE * 32, kOffAct = TILE * (32 + kTraffic);
@@ -162,6 +165,14 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
 
     const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full);
     const uint64_t pol = ACAS2D_LOAD_HINT ? l2_evict_first_policy() : 0;
+    // L2 RESIDENCY for a slice of the state.  Every step sweeps the same player records (36 B per env, rewritten in
+    // place) and streams 69 B per env of outputs past them; 4 Mi envs are 151 MB of state against a 126 MB L2, so
+    // left alone nothing survives from one launch to the next.  The first `keep_tiles` tiles are therefore loaded and
+    // stored with an evict_last policy: ~27 MB of state stay in L2 across launches (what the hint retains on this part,
+    // tools/ubench_l2keep.cu), are neither fetched from nor written back to HBM, and everything else keeps streaming
+    // with evict_first as before.  Worth 2 % here (79.1 -> 77.3 us; a plain copy kernel gains 12 %): with the HBM time
+    // down, the step is held by its own latency -- 63 % issue utilisation at four warps per scheduler.
+    const uint64_t pol_keep = l2_evict_last_policy();
     // tile schedule: round-robin over the grid (the CTAs sweep one contiguous window of HBM together), or
     // -DACAS2D_BLOCKED_TILES: each CTA streams through its own contiguous range (experiment)
 #ifdef ACAS2D_BLOCKED_TILES
@@ -174,11 +185,12 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
     auto issue = [&](long long tile, int s) {
         const uint32_t base = smem_base + s * kStageBytes, bar = full_base + 8 * s;
         const long long e0 = tile * kTileEnvs;
+        const uint64_t ps = tile < keep_tiles ? pol_keep : pol;
         mbar_expect_tx(bar, kStageBytes);
-        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, bar, pol);
-        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, bar, pol);
-        if (COMPACT) tma_load_1d(base + kOffThot, S.tpsi0 + e0, kTileEnvs * 4, bar, pol);
-        else tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar, pol);
+        tma_load_1d(base, S.ppos + e0, kTileEnvs * 16, bar, ps);
+        tma_load_1d(base + kOffPaux, S.paux + e0, kTileEnvs * 16, bar, ps);
+        if (COMPACT) tma_load_1d(base + kOffThot, S.tpsi0 + e0, kTileEnvs * 4, bar, ps);
+        else tma_load_1d(base + kOffThot, S.thot + e0, kTileEnvs * 16, bar, ps);
         tma_load_1d(base + kOffAct, actions + e0, kTileEnvs * 4, bar, pol);
     };
 
@@ -198,7 +210,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
 
     Tally tally;
     tally_clear(tally);
-    auto finish = [&](Env1 &e, float a, int64_t i) {
+    auto finish = [&](Env1 &e, float a, int64_t i, bool keep) {
         e.minsep = 0.0f;
         e.respawned = false;
         if (step_env1<false, true, true>(P, S, e, a, i, out, tally, nullptr)) {
@@ -206,7 +218,8 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
             if (slot < kRespawnQueue) { queue[slot] = i; return; }
             respawn_env1<true>(P, S, e, i, out);           // queue full (a whole tile finishing at once): in line
         }
-        store_env1(S, i, e, false);
+        if (keep) store_env1_hinted(S, i, e, pol_keep);
+        else store_env1(S, i, e, false);
     };
     int it = 0;
     for (long long tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
@@ -249,7 +262,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
                 }
             }
         }
-        finish(e, a, i);
+        finish(e, a, i, tile < keep_tiles);
     }
 
     // ragged tail (B % 256 envs): one CTA, plain loads
@@ -259,7 +272,7 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         if (i < S.B) {
             Env1 e;
             load_env1(S, i, e, false);
-            finish(e, __ldcs(actions + i), i);
+            finish(e, __ldcs(actions + i), i, false);
         }
     }
 
@@ -271,7 +284,8 @@ step_n1_tma_kernel(const DevParams P, const StatePtrs S, const float *__restrict
         Env1 e;
         e.minsep = 0.0f;
         respawn_env1<true>(P, S, e, i, out);
-        store_env1(S, i, e, false);
+        if (i < keep_tiles * kTileEnvs) store_env1_hinted(S, i, e, pol_keep);
+        else store_env1(S, i, e, false);
     }
     tally_flush_warp(S.stats, tally);
 }
@@ -304,8 +318,11 @@ int launch_n1_tma(const DevParams &P, const StatePtrs &S, const float *actions, 
     pdl.val.programmaticStreamSerializationAllowed = tuning().n1_pdl ? 1 : 0;
     lc.attrs = &pdl; lc.numAttrs = 1;
     const long long ft = full_tiles;
-    cudaError_t err = compact ? cudaLaunchKernelEx(&lc, step_n1_tma_kernel<STAGES, OCC, TILE, true>, P, S, actions, out, ft)
-                              : cudaLaunchKernelEx(&lc, step_n1_tma_kernel<STAGES, OCC, TILE, false>, P, S, actions, out, ft);
+    // tiles whose player state is kept L2-resident across launches (see the kernel): keep_mb of (36 B per env)
+    long long kt = (long long)((double)tuning().n1_keep_mb * 1e6 / (36.0 * kTileEnvs));
+    if (kt > full_tiles) kt = full_tiles;
+    cudaError_t err = compact ? cudaLaunchKernelEx(&lc, step_n1_tma_kernel<STAGES, OCC, TILE, true>, P, S, actions, out, ft, kt)
+                              : cudaLaunchKernelEx(&lc, step_n1_tma_kernel<STAGES, OCC, TILE, false>, P, S, actions, out, ft, kt);
     return err == cudaSuccess ? 0 : (int)err;
 }
 
