@@ -136,6 +136,10 @@ inline DevParams make_dev_params(const acas2d_params &p)
         const PlayerView v0 = player_view(d, p0, 1);
         d.reset_obs0 = v0.obs[0]; d.reset_obs2 = v0.obs[2]; d.reset_obs3 = v0.obs[3]; d.reset_obs4 = v0.obs[4];
     }
+    d.c_x0 = (double)(float)d.t0_x;
+    d.c_y0_up = (double)(float)d.t0_y_up;
+    d.c_y0_down = (double)(float)(d.t0_y_up + 1.0 * d.t0_y_span);
+    d.c_v = (double)(float)((d.factor_min + d.factor_span * 0.5) * p.airspeed);      // used only when factor_span == 0
     d.vrel_step = (float)(p.airspeed * dt * (1.0 + p.airspeed_factor_max) * (1.0 + 1e-6));
     d.coll_sure = (float)(2.0 * p.collision_radius - 1e-3);
     return d;
@@ -331,10 +335,10 @@ ACAS_HD bool compact_ok(const DevParams &P, const StatePtrs &S)
 
 ACAS_HD TrafficRec compact_traffic(const DevParams &P, float psi, bool down)
 {
-    TrafficRec t;
-    t.x0 = (double)(float)P.t0_x;
-    t.y0 = (double)(float)(P.t0_y_up + (down ? 1.0 : 0.0) * P.t0_y_span);
-    t.v = (double)(float)((P.factor_min + P.factor_span * 0.5) * P.airspeed);      // factor_span == 0 here
+    TrafficRec t;                                       // the float32 roundings are done once, in make_dev_params
+    t.x0 = P.c_x0;
+    t.y0 = down ? P.c_y0_down : P.c_y0_up;
+    t.v = P.c_v;                                        // factor_span == 0 here
     t.psi = (double)psi;
     return t;
 }

@@ -75,6 +75,7 @@ struct DevParams {
     float coll_sure_d2;     // (2*COLLISION_RADIUS - 0.05)^2: a float32 separation estimate below this IS a collision
     float dt_f;
     float reset_obs0, reset_obs2, reset_obs3, reset_obs4;   // player-only observation entries of a NEW game (all but the heading)
+    double c_x0, c_y0_up, c_y0_down, c_v;   // intruder 0's spawn pattern as a spawn stores it: rounded to float32 (compact form)
     float vrel_step;        // upper bound of the player-intruder relative displacement per step (spawned speeds), rounded up
     float coll_sure;        // 2*COLLISION_RADIUS - 1e-3: a separation bound below this proves a collision
 };
@@ -389,7 +390,7 @@ ACAS_HD PlayerView player_view(const DevParams &P, const Player &p, int32_t step
     PlayerView v;
     const double gx = P.goal_x - p.x, gy = P.goal_y - p.y;
     v.dg2 = gx * gx + gy * gy;
-    v.d_goal = acas_sqrtf((float)v.dg2);
+    v.d_goal = acas_sqrtf(acas_d2f_pos(v.dg2));
     // heading_to_goal (game.py:171-173, kinematics.py:16-22): degrees(atan2 mod 2pi) = 360 * turns
     const float gyf = (float)gy;
     const float phi_turns = atan2_turns(gyf, (float)gx);
