@@ -718,6 +718,42 @@ def test_on_device_episode_records_match_the_reference_lists(cuda):
             assert abs(row["Total Reward"] - g.total_reward) < parity.TOL_RETURN
 
 
+def test_episode_records_across_auto_resets(cuda):
+    """The trace kernel under SB3 semantics (auto-reset inside the step): a finished game's last row carries the done
+    flag, the next rows are the NEW game's initial row (steps == 1, a_lat == 0, reward 0: game.py:132-160) and its
+    first step (steps == 2); rewards and flags in the rows are the step's own outputs."""
+    from gym_ACAS2D.envs import _native
+    B, T = 256, 80
+    env = make(B, 1, seed=31, auto_reset=True)
+    env.reset()
+    ex = env.extract_state()
+    ex["steps"][:] = 1000 - (np.arange(B) % 60)                 # every game times out somewhere inside the window
+    env.inject_state(ex["player"], ex["traffic"], ex["steps"], ex["total_reward"])
+    env.enable_trace(B, 0, capacity=4 * T)
+    F = {k: i for i, k in enumerate(_native.TRACE_FIELDS)}
+    rewards, flags = [], []
+    for t in range(T):
+        o, r, d = env.step(env.random_actions(t, action_seed=8))
+        rewards.append(npy(r).copy()); flags.append(npy(env.flags).copy())
+    rows, count = env.trace_rows()
+    rewards, flags = np.array(rewards), np.array(flags)
+    ended = 0
+    for b in range(B):
+        rb = rows[b, : count[b]]
+        step_rows = rb[~((rb[:, F["steps"]] == 1))]             # initial rows have steps == 1; step rows follow the step order
+        assert len(step_rows) == T
+        assert np.array_equal(step_rows[:, F["flags"]].astype(np.uint8) & 15, flags[:, b] & 15)
+        assert np.abs(step_rows[:, F["reward"]] - rewards[:, b]).max() == 0.0
+        for k in np.flatnonzero(rb[:-1, F["flags"]].astype(np.int64) & 8):          # a done row ...
+            nxt = rb[k + 1]
+            assert nxt[F["steps"]] == 1 and nxt[F["a_lat"]] == 0 and nxt[F["reward"]] == 0            # ... then a new game's initial row
+            assert (nxt[F["x"]], nxt[F["y"]]) == (48.0, 500.0)
+            if k + 2 < len(rb):
+                assert rb[k + 2][F["steps"]] == 2
+            ended += 1
+    assert ended >= B - 4                                        # (a game ending on the window's last step has no successor row)
+
+
 def test_headless_render_frame(cuda):
     """debug frame of one env -- sky, goal disc + yellow GOAL_RADIUS ring, player disc + red
     COLLISION_RADIUS ring, intruder disc + ring, at the positions of the device state."""
