@@ -153,7 +153,7 @@ player_phase_kernel(const DevParams P, const StatePtrs S, const float *__restric
 #define ACAS2D_TILED_MIN_BLOCKS 7        /* 16-byte records: 7 blocks/SM at 72 registers (measured best in round 1) */
 #endif
 #ifndef ACAS2D_TILED_MIN_BLOCKS_KIN
-#define ACAS2D_TILED_MIN_BLOCKS_KIN 6
+#define ACAS2D_TILED_MIN_BLOCKS_KIN 7        /* measured: 5 -> 133.3, 6 -> 125.5, 7 -> 123.9, 8 -> 124.5 us (N = 64, 262 144 envs) */
 #endif
 
 template <int G, bool MINSEP, bool KIN>
