@@ -1086,8 +1086,15 @@ int launch_ppo_grad(const acas2d_ppo_config *cfg, const float *params, const flo
     PpoBatch b;
     b.obs = obs; b.actions = actions; b.old_logp = old_logp; b.adv = advantages; b.ret = returns;
     b.idx = indices; b.mb = minibatch;
-    ppo_grad_kernel<<<dim3((unsigned)ctas, 2), kPpoThreads, kPpoSmemBytes, st>>>(
-        params, b, cfg->normalize_advantage, cfg->clip_range, cfg->vf_coef, workspace + ACAS2D_PPO_WORKSPACE_HEAD, adam_step);
+    // programmatic dependent of whatever precedes it in the stream (the previous step's update kernel signals early)
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)ctas, 2); lc.blockDim = dim3(kPpoThreads); lc.dynamicSmemBytes = kPpoSmemBytes; lc.stream = st;
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = &pdl; lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, ppo_grad_kernel, params, b, (int)cfg->normalize_advantage, cfg->clip_range, cfg->vf_coef,
+                       workspace + ACAS2D_PPO_WORKSPACE_HEAD, adam_step);
     return ctas;
 }
 }  // namespace

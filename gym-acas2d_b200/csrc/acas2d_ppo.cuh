@@ -156,28 +156,6 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
     };
     prefetch(blockIdx.x);
 
-    {   // W2[j][i], rows as SB3 stores them, and its transpose; W1: 128-bit loads, all in flight
-        float4 v2[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) v2[it] = ((const float4 *)(w + kPolW2))[t + kPpoThreads * it];
-        float4 v1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (t < 128) v1 = ((const float4 *)(w + kPolW1))[t];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int e = 4 * (t + kPpoThreads * it), j = e >> 6, i = e & 63;
-            *(float4 *)(sW2 + j * kPpoLd + i) = v2[it];
-            sW2T[(i + 0) * kPpoLd + j] = v2[it].x; sW2T[(i + 1) * kPpoLd + j] = v2[it].y;
-            sW2T[(i + 2) * kPpoLd + j] = v2[it].z; sW2T[(i + 3) * kPpoLd + j] = v2[it].w;
-        }
-        if (t < 128) *(float4 *)(sW1 + (t >> 1) * kPpoLdW1 + 4 * (t & 1)) = v1;
-    }
-    if (t < 64) { sb1[t] = w[kPolB1 + t]; sb2[t] = w[kPolB2 + t]; sw3[t] = w[kPolW3 + t]; }
-    const float b3 = w[kPolB3];
-    const float log_std = params[kPpoLogStd];
-    const float inv_var = __expf(-2.0f * log_std);
-    const float inv_mb = 1.0f / (float)b.mb;
-    if (adam_step && blockIdx.x == 0 && net == 0 && t == 0) *adam_step += 1;     // nobody reads it in this kernel
-
     // SB3 ppo.py: advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8) over the minibatch
     // (std with Bessel's correction).  Every actor CTA computes it itself, in the same order.
     float adv_mean = 0.0f, adv_scale = 1.0f;
@@ -209,6 +187,33 @@ ppo_grad_kernel(const float *__restrict__ params, const PpoBatch b, const int no
         adv_mean = (float)mean;
         adv_scale = 1.0f / ((float)sqrt(var) + 1e-8f);
     }
+
+    // Programmatic dependent launch: everything above reads rollout data only and may overlap the tail of the update
+    // kernel of the previous gradient step (38 CTAs: most SMs are free while it runs).  The parameters it writes, the
+    // partial rows it reads and the step counter are touched only from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    {   // W2[j][i], rows as SB3 stores them, and its transpose; W1: 128-bit loads, all in flight
+        float4 v2[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) v2[it] = ((const float4 *)(w + kPolW2))[t + kPpoThreads * it];
+        float4 v1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (t < 128) v1 = ((const float4 *)(w + kPolW1))[t];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int e = 4 * (t + kPpoThreads * it), j = e >> 6, i = e & 63;
+            *(float4 *)(sW2 + j * kPpoLd + i) = v2[it];
+            sW2T[(i + 0) * kPpoLd + j] = v2[it].x; sW2T[(i + 1) * kPpoLd + j] = v2[it].y;
+            sW2T[(i + 2) * kPpoLd + j] = v2[it].z; sW2T[(i + 3) * kPpoLd + j] = v2[it].w;
+        }
+        if (t < 128) *(float4 *)(sW1 + (t >> 1) * kPpoLdW1 + 4 * (t & 1)) = v1;
+    }
+    if (t < 64) { sb1[t] = w[kPolB1 + t]; sb2[t] = w[kPolB2 + t]; sw3[t] = w[kPolW3 + t]; }
+    const float b3 = w[kPolB3];
+    const float log_std = params[kPpoLogStd];
+    const float inv_var = __expf(-2.0f * log_std);
+    const float inv_mb = 1.0f / (float)b.mb;
+    if (adam_step && blockIdx.x == 0 && net == 0 && t == 0) *adam_step += 1;     // nobody reads it in this kernel
 
     // gradient accumulators, kept in registers across this CTA's tiles
     float gW2[4][4] = {};                    // dW2[4 jg + q][4 ig + r]   (jg = t >> 4, ig = t & 15)
@@ -567,6 +572,7 @@ ppo_update_kernel(float *__restrict__ params, const float *__restrict__ partials
 {
     __shared__ float red[32];
     __shared__ unsigned long long s_before;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       // the next step's gradient kernel may begin its gathers
     const int t = threadIdx.x, sub = t & 3, p = blockIdx.x * 256 + (t >> 2);
     const bool owner = sub == 0 && p < kPpoParams;
     const int step = sync[0];
