@@ -355,6 +355,11 @@ int acas2d_ppo_adam(const acas2d_ppo_config *cfg, float *params, const float *gr
  * rank publishes its gradient in its own block (double-buffered by step parity), signals every peer with a
  * release store, waits for all peers' signals and sums the blocks in rank order -- every rank applies the
  * bit-identical mean gradient and no NCCL call is made.  world == 1: rank 0, peer_exchange NULL.
+ * Stream ordering note: the gradient kernel is launched as a PROGRAMMATIC DEPENDENT (it overlaps its gathers of obs /
+ * actions / old_logp / advantages / returns / indices with the tail of the kernel before it when that kernel signals
+ * early: this library's update kernel and its environment step kernels do).  Do not pass, as those six arrays, buffers
+ * that the IMMEDIATELY preceding launch on the stream writes (e.g. the obs buffer of an acas2d_step issued right
+ * before); rollout buffers filled by acas2d_policy_step* and anything separated by another launch are fine.
  * The update kernel is a COOPERATIVE launch (its CTAs wait on each other): if the device cannot hold all of them
  * at once the call returns the launch error (cudaErrorCooperativeLaunchTooLarge) instead of dead-locking. */
 #define ACAS2D_PPO_ERR_BARRIER 1   /* sync[1]: a grid barrier of the update kernel timed out */
